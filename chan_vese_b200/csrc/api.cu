@@ -1,0 +1,1088 @@
+// C ABI of chan_vese_b200 (include/chan_vese_b200.h): contexts, resident jobs (sessions / batches),
+// one-shot calls on host buffers, the multi-GPU row-slab plumbing (NCCL, loaded at run time).
+// All compute is in csv_kernels.cu / pm_kernels.cu; there is no CPU fallback anywhere in this file.
+#include <dlfcn.h>
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/chan_vese_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace cvb;
+
+// ---- NCCL, bound at run time so that the library loads (and the host helpers work) without it -----------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclUint8 = 1, ncclFloat64 = 8 };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static bool load_nccl(std::string &err) {
+    if (g_nccl.handle) return true;
+    const char *names[] = {getenv("CVB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        err = std::string("cannot load NCCL: ") + dlerror();
+        return false;
+    }
+#define CVB_SYM(field, name)                                         \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                      \
+    if (!g_nccl.field) {                                             \
+        err = std::string("NCCL symbol missing: ") + name;           \
+        return false;                                                \
+    }
+    CVB_SYM(GetUniqueId, "ncclGetUniqueId")
+    CVB_SYM(CommInitRank, "ncclCommInitRank")
+    CVB_SYM(CommDestroy, "ncclCommDestroy")
+    CVB_SYM(AllGather, "ncclAllGather")
+    CVB_SYM(Send, "ncclSend")
+    CVB_SYM(Recv, "ncclRecv")
+    CVB_SYM(GroupStart, "ncclGroupStart")
+    CVB_SYM(GroupEnd, "ncclGroupEnd")
+    CVB_SYM(GetErrorString, "ncclGetErrorString")
+#undef CVB_SYM
+    g_nccl.handle = h;
+    return true;
+}
+
+// ---- objects ----------------------------------------------------------------------------------------------
+struct cvb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    cvb_math_mode math = CVB_MATH_FAST;
+    int tile_rows = 0;
+    cvb_stats stats{};
+    double *d_atan_tab = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+struct Job {
+    cvb_context *ctx = nullptr;
+    Geom g{};
+    cvb_precision prec = CVB_PRECISION_F64;
+    uint8_t *d_img = nullptr;
+    uint8_t *d_img_saved = nullptr;  // cvb_*_save_image
+    double *d_u[2] = {nullptr, nullptr};
+    double *d_pm[2] = {nullptr, nullptr};
+    double *d_aux = nullptr;  // one fp64 plane set (curvature output), lazy
+    CsvState *d_state = nullptr;
+    CsvState *h_state = nullptr;  // pinned, 2 * count
+    double *d_partials = nullptr;
+    double *d_group = nullptr;
+    signed char *d_sign = nullptr;  // checkerboard sign vectors
+    int ngroups_local = 0;
+    int group_lo = 0, group_hi = NGROUPS;  // groups owned by this rank
+    bool slab = false;
+};
+struct cvb_session : Job {};
+struct cvb_batch : Job {};
+
+static thread_local std::string g_create_err;
+
+static cvb_status fail(cvb_context *ctx, cvb_status st, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_err = buf;
+    return st;
+}
+#define CU(ctx, expr)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? CVB_ERR_OUT_OF_MEMORY : CVB_ERR_CUDA,    \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);    \
+    } while (0)
+#define NC(ctx, expr)                                                                                    \
+    do {                                                                                                 \
+        int r__ = (expr);                                                                                \
+        if (r__ != 0)                                                                                    \
+            return fail(ctx, CVB_ERR_COMM, "%s failed: %s", #expr, g_nccl.GetErrorString(r__));         \
+    } while (0)
+#define TRY(expr)                          \
+    do {                                   \
+        cvb_status s__ = (expr);           \
+        if (s__ != CVB_OK) return s__;     \
+    } while (0)
+
+// ---- host-side helpers (no GPU) ---------------------------------------------------------------------------
+extern "C" const char *cvb_version(void) { return "chan_vese_b200 0.1 (sm_100a)"; }
+
+extern "C" int cvb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// src/main.cpp:498: for (double t = 0; t < T; t += L)
+extern "C" int cvb_pm_num_steps(double L, double T) {
+    if (!(L > 0.0)) return -1;
+    int n = 0;
+    for (double t = 0; t < T; t += L) {
+        if (n == INT_MAX) return -1;
+        ++n;
+    }
+    return n;
+}
+
+static const double kPi = 3.14159265358979323846;  // boost::math::constants::pi<double>()
+static signed char sign_of(double p) { return (signed char)((p > 0) - (p < 0)); }
+
+// src/main.cpp:221-233: sign(sin(pi*i/5) * sin(pi*j/5)), glibc sin on the host
+extern "C" cvb_status cvb_levelset_checkerboard(int h, int w, double *u) {
+    if (h <= 0 || w <= 0 || !u) return CVB_ERR_INVALID_ARGUMENT;
+    std::vector<double> sj(w);
+    for (int j = 0; j < w; ++j) sj[j] = sin(kPi * j / 5);
+    for (int i = 0; i < h; ++i) {
+        const double si = sin(kPi * i / 5);
+        for (int j = 0; j < w; ++j) u[(size_t)i * w + j] = (double)sign_of(si * sj[j]);
+    }
+    return CVB_OK;
+}
+// InteractiveDataRect::get_levelset, src/InteractiveDataRect.cpp:20-27
+extern "C" cvb_status cvb_levelset_rect(int h, int w, int x, int y, int rw, int rh, double *u) {
+    if (h <= 0 || w <= 0 || !u) return CVB_ERR_INVALID_ARGUMENT;
+    memset(u, 0, sizeof(double) * (size_t)h * w);
+    for (int i = (y < 0 ? 0 : y); i < y + rh && i < h; ++i)
+        for (int j = (x < 0 ? 0 : x); j < x + rw && j < w; ++j) u[(size_t)i * w + j] = 1.0;
+    return CVB_OK;
+}
+// InteractiveDataCirc::get_levelset, src/InteractiveDataCirc.cpp:18-25: cv::circle(u, c, r, 1) with the default
+// thickness 1 = the 8-way symmetric midpoint circle, clipped to the image.
+extern "C" cvb_status cvb_levelset_circ(int h, int w, int cx, int cy, int radius, double *u) {
+    if (h <= 0 || w <= 0 || !u || radius < 0) return CVB_ERR_INVALID_ARGUMENT;
+    memset(u, 0, sizeof(double) * (size_t)h * w);
+    auto put = [&](int px, int py) {
+        if (px >= 0 && px < w && py >= 0 && py < h) u[(size_t)py * w + px] = 1.0;
+    };
+    int dx = radius, dy = 0, err = 0, inc = 1, dec = 2 * radius - 1;
+    while (dx >= dy) {
+        put(cx - dx, cy - dy); put(cx - dx, cy + dy); put(cx + dx, cy - dy); put(cx + dx, cy + dy);
+        put(cx - dy, cy - dx); put(cx - dy, cy + dx); put(cx + dy, cy - dx); put(cx + dy, cy + dx);
+        ++dy;
+        err += inc;
+        inc += 2;
+        if (err > 0) {
+            err -= dec;
+            --dx;
+            dec -= 2;
+        }
+    }
+    return CVB_OK;
+}
+
+static int auto_seg_rows(int h, int w, int count) {
+    const long long target = 2LL * 148 * 4;  // two waves of 4 CTAs per SM
+    const int ncb = ceil_div(w, CSV_CB);
+    const int cands[] = {32, 16, 8, 4};
+    for (int s : cands)
+        if ((long long)count * ceil_div(h, s) * ncb >= target) return s;
+    return 4;
+}
+extern "C" int cvb_auto_tile_rows(int h, int w, int count) {
+    if (h <= 0 || w <= 0 || count <= 0) return 0;
+    return auto_seg_rows(h, w, count);
+}
+extern "C" cvb_status cvb_slab_partition(int h, int tile_rows, int nranks, int rank, int *row_lo, int *row_hi) {
+    if (h <= 0 || tile_rows <= 0 || nranks <= 0 || rank < 0 || rank >= nranks || NGROUPS % nranks != 0 || !row_lo ||
+        !row_hi)
+        return CVB_ERR_INVALID_ARGUMENT;
+    const int nseg = ceil_div(h, tile_rows);
+    const int g0 = rank * (NGROUPS / nranks), g1 = (rank + 1) * (NGROUPS / nranks);
+    const int s0 = group_seg_begin(g0, nseg), s1 = group_seg_begin(g1, nseg);
+    *row_lo = std::min(s0 * tile_rows, h);
+    *row_hi = std::min(s1 * tile_rows, h);
+    return (*row_hi > *row_lo) ? CVB_OK : CVB_ERR_INVALID_ARGUMENT;
+}
+
+// ---- context ------------------------------------------------------------------------------------------------
+extern "C" cvb_status cvb_context_create(int device, void *stream, cvb_context **out) {
+    if (!out) return fail(nullptr, CVB_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    int n = cvb_device_count();
+    if (n <= 0) return fail(nullptr, CVB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= n) return fail(nullptr, CVB_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, n);
+    CU(nullptr, cudaSetDevice(device));
+    cvb_context *c = new cvb_context;
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return fail(nullptr, CVB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        c->own_stream = true;
+    }
+    for (auto &e : c->ev) cudaEventCreate(&e);
+    // atan(c_q)/pi table of math.cuh, from the host libm
+    double tab[34];
+    tab[0] = 0.0;
+    for (int q = 0; q < 32; ++q) {
+        const uint64_t bits = ((uint64_t)(((1019u * 4u + (unsigned)q) << 18) | 0x00020000u)) << 32;
+        double cq;
+        memcpy(&cq, &bits, 8);
+        tab[1 + q] = atan(cq) / kPi;
+    }
+    tab[33] = 0.5;
+    if (cudaMalloc(&c->d_atan_tab, sizeof tab) != cudaSuccess ||
+        cudaMemcpy(c->d_atan_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cvb_status st = fail(nullptr, CVB_ERR_CUDA, "context set-up: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return st;
+    }
+    *out = c;
+    return CVB_OK;
+}
+extern "C" void cvb_context_destroy(cvb_context *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->d_atan_tab);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" const char *cvb_last_error(const cvb_context *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+extern "C" cvb_status cvb_context_set_math_mode(cvb_context *c, cvb_math_mode m) {
+    if (!c || (m != CVB_MATH_FAST && m != CVB_MATH_STRICT)) return CVB_ERR_INVALID_ARGUMENT;
+    c->math = m;
+    return CVB_OK;
+}
+extern "C" cvb_status cvb_context_set_tile_rows(cvb_context *c, int rows) {
+    if (!c || rows < 0 || rows > 4096) return CVB_ERR_INVALID_ARGUMENT;
+    c->tile_rows = rows;
+    return CVB_OK;
+}
+extern "C" cvb_status cvb_context_get_stats(cvb_context *c, cvb_stats *out) {
+    if (!c || !out) return CVB_ERR_INVALID_ARGUMENT;
+    *out = c->stats;
+    return CVB_OK;
+}
+extern "C" cvb_status cvb_context_reset_stats(cvb_context *c) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    c->stats = cvb_stats{};
+    return CVB_OK;
+}
+extern "C" cvb_status cvb_context_synchronize(cvb_context *c) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
+}
+extern "C" cvb_status cvb_host_alloc(size_t bytes, void **out) {
+    if (!out) return CVB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return CVB_ERR_OUT_OF_MEMORY;
+    }
+    return CVB_OK;
+}
+extern "C" void cvb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- multi-GPU plumbing ---------------------------------------------------------------------------------------
+extern "C" cvb_status cvb_comm_create_id(cvb_context *c, void *id_out) {
+    if (!c || !id_out) return CVB_ERR_INVALID_ARGUMENT;
+    if (!load_nccl(c->err)) return CVB_ERR_COMM;
+    ncclUniqueId id;
+    NC(c, g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return CVB_OK;
+}
+extern "C" cvb_status cvb_comm_init(cvb_context *c, const void *id, int nranks, int rank) {
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks || NGROUPS % nranks != 0)
+        return fail(c, CVB_ERR_INVALID_ARGUMENT, "nranks must divide %d", NGROUPS);
+    if (c->comm) return fail(c, CVB_ERR_STATE, "communicator already initialised");
+    if (!load_nccl(c->err)) return CVB_ERR_COMM;
+    CU(c, cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    NC(c, g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
+    c->nranks = nranks;
+    c->rank = rank;
+    return CVB_OK;
+}
+extern "C" cvb_status cvb_comm_destroy(cvb_context *c) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    if (c->comm) {
+        cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    c->nranks = 1;
+    c->rank = 0;
+    return CVB_OK;
+}
+
+// Exchange HALO rows with the slab above and below: my top halo <- last rows of rank-1, my bottom halo <- first
+// rows of rank+1.  base points at plane 0; elem = bytes per element.
+static cvb_status exchange_halo(Job *j, void *base, size_t elem, int nplanes) {
+    cvb_context *c = j->ctx;
+    if (!j->slab || c->nranks == 1) return CVB_OK;
+    const Geom &g = j->g;
+    const size_t rowb = (size_t)g.pitch * elem, hb = rowb * HALO;
+    const int rows = g.row_hi - g.row_lo;
+    NC(c, g_nccl.GroupStart());
+    for (int p = 0; p < nplanes; ++p) {
+        char *pl = (char *)base + (size_t)p * g.plane_elems * elem;
+        if (c->rank > 0) {
+            NC(c, g_nccl.Send(pl + hb, hb, ncclUint8, c->rank - 1, c->comm, c->stream));              // my first rows up
+            NC(c, g_nccl.Recv(pl, hb, ncclUint8, c->rank - 1, c->comm, c->stream));                   // top halo
+        }
+        if (c->rank < c->nranks - 1) {
+            NC(c, g_nccl.Send(pl + rowb * rows, hb, ncclUint8, c->rank + 1, c->comm, c->stream));     // my last rows down
+            NC(c, g_nccl.Recv(pl + rowb * (rows + HALO), hb, ncclUint8, c->rank + 1, c->comm, c->stream));
+        }
+    }
+    NC(c, g_nccl.GroupEnd());
+    return CVB_OK;
+}
+
+// ---- jobs -------------------------------------------------------------------------------------------------------
+static void job_free(Job *j) {
+    if (!j) return;
+    cudaSetDevice(j->ctx->device);
+    cudaStreamSynchronize(j->ctx->stream);
+    cudaFree(j->d_img);
+    cudaFree(j->d_img_saved);
+    cudaFree(j->d_u[0]);
+    cudaFree(j->d_u[1]);
+    cudaFree(j->d_pm[0]);
+    cudaFree(j->d_pm[1]);
+    cudaFree(j->d_aux);
+    cudaFree(j->d_state);
+    cudaFree(j->d_partials);
+    cudaFree(j->d_group);
+    cudaFree(j->d_sign);
+    if (j->h_state) cudaFreeHost(j->h_state);
+}
+
+static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int w, int row_lo, int row_hi, bool slab,
+                           cvb_precision prec) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    if (count <= 0 || (n != 1 && n != 3) || h <= 0 || w <= 0)
+        return fail(c, CVB_ERR_INVALID_ARGUMENT, "bad job shape: count=%d n=%d h=%d w=%d (n must be 1 or 3)", count, n, h, w);
+    if (prec != CVB_PRECISION_F64)
+        return fail(c, CVB_ERR_INVALID_ARGUMENT, "only CVB_PRECISION_F64 is implemented in this build");
+    if (row_lo < 0 || row_hi > h || row_lo >= row_hi) return fail(c, CVB_ERR_INVALID_ARGUMENT, "bad slab rows [%d,%d)", row_lo, row_hi);
+    CU(c, cudaSetDevice(c->device));
+    j->ctx = c;
+    j->prec = prec;
+    j->slab = slab;
+    Geom &g = j->g;
+    g.h = h;
+    g.w = w;
+    g.row_lo = row_lo;
+    g.row_hi = row_hi;
+    g.pitch = (w + 15) / 16 * 16;
+    g.rows_alloc = row_hi - row_lo + 2 * HALO;
+    g.nch = n;
+    g.count = count;
+    g.seg_rows = c->tile_rows > 0 ? c->tile_rows : auto_seg_rows(h, w, count);
+    g.nseg_global = ceil_div(h, g.seg_rows);
+    if (row_lo % g.seg_rows != 0 || (row_hi != h && row_hi % g.seg_rows != 0))
+        return fail(c, CVB_ERR_INVALID_ARGUMENT, "slab rows [%d,%d) are not aligned to tile_rows=%d (use cvb_slab_partition)",
+                    row_lo, row_hi, g.seg_rows);
+    g.seg0 = row_lo / g.seg_rows;
+    g.nseg = ceil_div(row_hi, g.seg_rows) - g.seg0;
+    g.ncb_csv = ceil_div(w, CSV_CB);
+    g.ncb_pm = ceil_div(w, PM_CB);
+    g.plane_elems = (long long)g.rows_alloc * g.pitch;
+    if ((long long)count * n * g.nseg * std::max(g.ncb_csv, g.ncb_pm) > 0x7fffffffLL)
+        return fail(c, CVB_ERR_INVALID_ARGUMENT, "job too large for one launch");
+    // groups owned by this job
+    j->ngroups_local = 0;
+    j->group_lo = NGROUPS;
+    j->group_hi = 0;
+    for (int grp = 0; grp < NGROUPS; ++grp) {
+        const int sb = std::max(group_seg_begin(grp, g.nseg_global), g.seg0);
+        const int se = std::min(group_seg_begin(grp + 1, g.nseg_global), g.seg0 + g.nseg);
+        if (se > sb) {
+            ++j->ngroups_local;
+            j->group_lo = std::min(j->group_lo, grp);
+            j->group_hi = std::max(j->group_hi, grp + 1);
+            // a group must not straddle two ranks
+            if (group_seg_begin(grp, g.nseg_global) < g.seg0 || group_seg_begin(grp + 1, g.nseg_global) > g.seg0 + g.nseg)
+                return fail(c, CVB_ERR_INVALID_ARGUMENT, "slab rows [%d,%d) split reduction group %d (use cvb_slab_partition)",
+                            row_lo, row_hi, grp);
+        }
+    }
+    const size_t pe = (size_t)g.plane_elems;
+    CU(c, cudaMalloc(&j->d_img, (size_t)count * n * pe));
+    CU(c, cudaMalloc(&j->d_u[0], (size_t)count * pe * sizeof(double)));
+    CU(c, cudaMalloc(&j->d_u[1], (size_t)count * pe * sizeof(double)));
+    CU(c, cudaMalloc(&j->d_state, (size_t)count * sizeof(CsvState)));
+    const size_t npart = (size_t)count * g.nseg * g.ncb_csv * WARPS_PER_CTA * NACC;
+    CU(c, cudaMalloc(&j->d_partials, npart * sizeof(double)));
+    CU(c, cudaMalloc(&j->d_group, (size_t)NGROUPS * count * NACC * sizeof(double)));
+    CU(c, cudaMallocHost(&j->h_state, 2 * (size_t)count * sizeof(CsvState)));
+    CU(c, cudaMemsetAsync(j->d_img, 0, (size_t)count * n * pe, c->stream));
+    CU(c, cudaMemsetAsync(j->d_u[0], 0, (size_t)count * pe * sizeof(double), c->stream));
+    CU(c, cudaMemsetAsync(j->d_u[1], 0, (size_t)count * pe * sizeof(double), c->stream));
+    CU(c, cudaMemsetAsync(j->d_state, 0, (size_t)count * sizeof(CsvState), c->stream));
+    CU(c, cudaMemsetAsync(j->d_partials, 0, npart * sizeof(double), c->stream));
+    CU(c, cudaMemsetAsync(j->d_group, 0, (size_t)NGROUPS * count * NACC * sizeof(double), c->stream));
+    return CVB_OK;
+}
+
+static void fill_args(const Job *j, const cvb_csv_params *p, double tol, CsvArgs &A) {
+    memset(&A, 0, sizeof A);
+    A.u[0] = j->d_u[0];
+    A.u[1] = j->d_u[1];
+    A.img = j->d_img;
+    A.state = j->d_state;
+    A.partials = j->d_partials;
+    A.group_sums = j->d_group;
+    A.kappa_out = j->d_aux;
+    A.atan_tab = j->ctx->d_atan_tab;
+    A.eps = 1.0;
+    if (p) {
+        // src/main.cpp:985 as OpenCV's MatExpr executes it: addWeighted(kappa, mu*dt, u_diff, (1/N)*dt, -nu*dt)
+        A.alpha = p->mu * p->dt;
+        A.beta = (1.0 / j->g.nch) * p->dt;
+        A.gamma = (-p->nu) * p->dt;
+        A.eps = p->eps;
+        for (int k = 0; k < MAX_CH; ++k) {
+            A.lambda1[k] = p->lambda1[k];
+            A.lambda2[k] = p->lambda2[k];
+        }
+    }
+    A.tol = tol;
+    A.multi_rank = (j->slab && j->ctx->nranks > 1) ? 1 : 0;
+    A.ngroups_local = j->ngroups_local;
+    A.g = j->g;
+}
+
+// all-gather of the group sums + finalize (multi-rank only)
+static cvb_status reduce_across_ranks(Job *j, const CsvArgs &A, int mode) {
+    cvb_context *c = j->ctx;
+    if (!A.multi_rank) return CVB_OK;
+    const size_t per_rank = (size_t)(NGROUPS / c->nranks) * j->g.count * NACC;
+    NC(c, g_nccl.AllGather(j->d_group + per_rank * c->rank, j->d_group, per_rank, ncclFloat64, c->comm, c->stream));
+    CU(c, launch_csv_finalize(A, mode, c->stream));
+    c->stats.kernel_launches += 1;
+    return CVB_OK;
+}
+
+static cvb_status job_upload_image(Job *j, const uint8_t *const *planes) {
+    cvb_context *c = j->ctx;
+    if (!planes) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes is NULL");
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    const int rows = g.row_hi - g.row_lo;
+    for (int p = 0; p < g.count * g.nch; ++p) {
+        if (!planes[p]) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes[%d] is NULL", p);
+        CU(c, cudaMemcpy2DAsync(j->d_img + (size_t)p * g.plane_elems + (size_t)HALO * g.pitch, g.pitch, planes[p], g.w, g.w,
+                                rows, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (uint64_t)rows * g.w;
+    }
+    TRY(exchange_halo(j, j->d_img, 1, g.count * g.nch));
+    CU(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers on return
+    return CVB_OK;
+}
+// Perona-Malik smooths the resident planes in place; a saved copy lets a caller re-run from the original image
+// without another host-to-device transfer.
+static cvb_status job_save_image(Job *j) {
+    cvb_context *c = j->ctx;
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)j->g.count * j->g.nch * j->g.plane_elems;
+    if (!j->d_img_saved) CU(c, cudaMalloc(&j->d_img_saved, bytes));
+    CU(c, cudaMemcpyAsync(j->d_img_saved, j->d_img, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return CVB_OK;
+}
+static cvb_status job_restore_image(Job *j) {
+    cvb_context *c = j->ctx;
+    if (!j->d_img_saved) return fail(c, CVB_ERR_STATE, "no saved image (call save_image first)");
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)j->g.count * j->g.nch * j->g.plane_elems;
+    CU(c, cudaMemcpyAsync(j->d_img, j->d_img_saved, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return CVB_OK;
+}
+static cvb_status job_download_image(Job *j, int first_plane, int nplanes, uint8_t *const *planes) {
+    cvb_context *c = j->ctx;
+    if (!planes) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes is NULL");
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    const int rows = g.row_hi - g.row_lo;
+    for (int p = 0; p < nplanes; ++p) {
+        if (!planes[p]) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes[%d] is NULL", p);
+        CU(c, cudaMemcpy2DAsync(planes[p], g.w, j->d_img + (size_t)(first_plane + p) * g.plane_elems + (size_t)HALO * g.pitch,
+                                g.pitch, g.w, rows, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += (uint64_t)rows * g.w;
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
+}
+// u0 into buffer 0 of image `index` (or of all images when index < 0); resets the step counters
+static cvb_status job_upload_levelset(Job *j, int index, const double *u) {
+    cvb_context *c = j->ctx;
+    if (!u) return fail(c, CVB_ERR_INVALID_ARGUMENT, "u is NULL");
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    const int rows = g.row_hi - g.row_lo;
+    const int lo = index < 0 ? 0 : index, hi = index < 0 ? g.count : index + 1;
+    for (int m = lo; m < hi; ++m) {
+        double *dst = j->d_u[0] + (size_t)m * g.plane_elems + (size_t)HALO * g.pitch;
+        if (m == lo) {
+            CU(c, cudaMemcpy2DAsync(dst, g.pitch * sizeof(double), u, g.w * sizeof(double), g.w * sizeof(double), rows,
+                                    cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2d_bytes += (uint64_t)rows * g.w * sizeof(double);
+        } else {  // one u0 shared by all images: replicate on the device
+            CU(c, cudaMemcpyAsync(dst, j->d_u[0] + (size_t)lo * g.plane_elems + (size_t)HALO * g.pitch,
+                                  (size_t)rows * g.pitch * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
+    CU(c, cudaMemsetAsync(j->d_state + lo, 0, (size_t)(hi - lo) * sizeof(CsvState), c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffer on return
+    return CVB_OK;
+}
+static cvb_status job_fetch_state(Job *j) {
+    cvb_context *c = j->ctx;
+    CU(c, cudaMemcpyAsync(j->h_state, j->d_state, (size_t)j->g.count * sizeof(CsvState), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
+}
+static cvb_status job_download_levelset(Job *j, int index, double *u) {
+    cvb_context *c = j->ctx;
+    if (!u || index < 0 || index >= j->g.count) return fail(c, CVB_ERR_INVALID_ARGUMENT, "bad download arguments");
+    CU(c, cudaSetDevice(c->device));
+    TRY(job_fetch_state(j));
+    const Geom &g = j->g;
+    const int rows = g.row_hi - g.row_lo;
+    const double *src = j->d_u[j->h_state[index].steps_done & 1] + (size_t)index * g.plane_elems + (size_t)HALO * g.pitch;
+    CU(c, cudaMemcpy2DAsync(u, g.w * sizeof(double), src, g.pitch * sizeof(double), g.w * sizeof(double), rows,
+                            cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += (uint64_t)rows * g.w * sizeof(double);
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
+}
+static cvb_status job_mask(Job *j, int index, int invert, uint8_t *mask) {
+    cvb_context *c = j->ctx;
+    if (!mask || index < 0 || index >= j->g.count) return fail(c, CVB_ERR_INVALID_ARGUMENT, "bad mask arguments");
+    CU(c, cudaSetDevice(c->device));
+    TRY(job_fetch_state(j));
+    const Geom &g = j->g;
+    const int rows = g.row_hi - g.row_lo;
+    // the mask is written into the idle level-set buffer's storage (as bytes), then copied out
+    const int cur = j->h_state[index].steps_done & 1;
+    const double *src = j->d_u[cur] + (size_t)index * g.plane_elems + (size_t)HALO * g.pitch;
+    uint8_t *tmp = reinterpret_cast<uint8_t *>(j->d_u[cur ^ 1] + (size_t)index * g.plane_elems);
+    CU(c, launch_mask(src, tmp, rows, g.w, g.pitch, invert, c->stream));
+    c->stats.kernel_launches += 1;
+    CU(c, cudaMemcpy2DAsync(mask, g.w, tmp, g.pitch, g.w, rows, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += (uint64_t)rows * g.w;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
+}
+
+static cvb_status job_init_checkerboard(Job *j) {
+    cvb_context *c = j->ctx;
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    std::vector<signed char> s((size_t)g.h + g.w);
+    // sign(si*sj) = sign(si)*sign(sj) unless the product underflows to zero: |sin| >= ~1e-16 or exactly 0 here
+    for (int i = 0; i < g.h; ++i) s[i] = sign_of(sin(kPi * i / 5));
+    for (int jx = 0; jx < g.w; ++jx) s[(size_t)g.h + jx] = sign_of(sin(kPi * jx / 5));
+    if (!j->d_sign) CU(c, cudaMalloc(&j->d_sign, s.size()));
+    CU(c, cudaMemcpyAsync(j->d_sign, s.data(), s.size(), cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += s.size();
+    for (int m = 0; m < g.count; ++m) {
+        CU(c, launch_checkerboard(j->d_u[0] + (size_t)m * g.plane_elems, j->d_sign, j->d_sign + g.h, g.row_lo,
+                                  g.row_hi - g.row_lo, g.w, g.pitch, c->stream));
+        c->stats.kernel_launches += 1;
+    }
+    CU(c, cudaMemsetAsync(j->d_state, 0, (size_t)g.count * sizeof(CsvState), c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // s goes out of scope
+    return CVB_OK;
+}
+
+// perona_malik, src/main.cpp:478-560, on the resident image planes (in place)
+static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *steps) {
+    cvb_context *c = j->ctx;
+    if (!(L > 0.0) || !(K != 0.0)) return fail(c, CVB_ERR_INVALID_ARGUMENT, "perona_malik needs L > 0 and K != 0");
+    const int nsteps = cvb_pm_num_steps(L, T);
+    if (nsteps < 0) return fail(c, CVB_ERR_INVALID_ARGUMENT, "perona_malik step count overflows");
+    if (steps) *steps = nsteps;
+    if (nsteps == 0) return CVB_OK;  // the reference returns an unset image here; the planes are left unchanged
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    const int nplanes = g.count * g.nch;
+    const size_t bytes = (size_t)nplanes * g.plane_elems * sizeof(double);
+    for (int b = 0; b < (nsteps > 2 ? 2 : 1); ++b)
+        if (!j->d_pm[b]) {
+            CU(c, cudaMalloc(&j->d_pm[b], bytes));
+            CU(c, cudaMemsetAsync(j->d_pm[b], 0, bytes, c->stream));
+        }
+    const bool strict = c->math == CVB_MATH_STRICT;
+    PmArgs A;
+    A.K = K;
+    A.L = L;
+    A.g = g;
+    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    for (int s = 1; s <= nsteps; ++s) {
+        const bool first = s == 1, last = s == nsteps && nsteps >= 2;
+        A.in = first ? (const void *)j->d_img : (const void *)j->d_pm[(s - 2) & 1];
+        A.out = last ? (void *)j->d_img : (void *)j->d_pm[(s - 1) & 1];
+        CU(c, launch_pm_step(A, first, last, strict, c->stream));
+        c->stats.kernel_launches += 1;
+        c->stats.pm_step_launches += 1;
+        if (last)
+            TRY(exchange_halo(j, j->d_img, 1, nplanes));
+        else if (s < nsteps)
+            TRY(exchange_halo(j, j->d_pm[(s - 1) & 1], sizeof(double), nplanes));
+    }
+    if (nsteps == 1) {  // u8 -> fp64 -> u8: the single step cannot write the plane it reads
+        CU(c, launch_pm_quantise(j->d_pm[0], j->d_img, (size_t)nplanes * g.plane_elems, c->stream));
+        c->stats.kernel_launches += 1;
+        TRY(exchange_halo(j, j->d_img, 1, nplanes));
+    }
+    CU(c, cudaEventRecord(c->ev[1], c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->stats.pm_ms += ms;
+    return CVB_OK;
+}
+static void job_release_pm(Job *j) {
+    cudaFree(j->d_pm[0]);
+    cudaFree(j->d_pm[1]);
+    j->d_pm[0] = j->d_pm[1] = nullptr;
+}
+
+static cvb_status check_params(cvb_context *c, const cvb_csv_params *p) {
+    if (!p) return fail(c, CVB_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (!(p->eps > 0.0)) return fail(c, CVB_ERR_INVALID_ARGUMENT, "epsilon must be > 0");
+    return CVB_OK;
+}
+
+// sums of the current level set -> c1/c2 (mode 2) or the full set-up of a run (mode 1)
+static cvb_status job_csv_init(Job *j, const CsvArgs &A, int mode) {
+    cvb_context *c = j->ctx;
+    CU(c, launch_csv_init(A, mode, c->stream));
+    c->stats.kernel_launches += 1;
+    TRY(reduce_across_ranks(j, A, mode));
+    return CVB_OK;
+}
+static cvb_status job_csv_launch_step(Job *j, const CsvArgs &A, int step_index /* 0-based, for halo parity */) {
+    cvb_context *c = j->ctx;
+    const bool strict = c->math == CVB_MATH_STRICT;
+    CU(c, launch_csv_step(A, strict, c->stream));
+    c->stats.kernel_launches += 1;
+    c->stats.csv_step_launches += 1;
+    if (A.multi_rank) {
+        TRY(reduce_across_ranks(j, A, 0));
+        TRY(exchange_halo(j, j->d_u[(step_index + 1) & 1], sizeof(double), j->g.count));
+    }
+    return CVB_OK;
+}
+
+// The time-step loop, src/main.cpp:949-1001
+static cvb_status job_csv_run(Job *j, const cvb_csv_params *p, double tol, int max_steps, int *steps_done,
+                              double *last_norm, cvb_frame_fn frame, void *user) {
+    cvb_context *c = j->ctx;
+    TRY(check_params(c, p));
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    if (frame && (g.count != 1 || j->slab)) return fail(c, CVB_ERR_INVALID_ARGUMENT, "frame observer needs a whole single image");
+    CsvArgs A;
+    fill_args(j, p, tol, A);
+    // a run starts from the level set in buffer (steps_done & 1); move it to buffer 0 if needed
+    TRY(job_fetch_state(j));
+    for (int m = 0; m < g.count; ++m)
+        if (j->h_state[m].steps_done & 1)
+            CU(c, cudaMemcpyAsync(j->d_u[0] + (size_t)m * g.plane_elems, j->d_u[1] + (size_t)m * g.plane_elems,
+                                  (size_t)g.plane_elems * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (A.multi_rank) TRY(exchange_halo(j, j->d_u[0], sizeof(double), g.count));
+    TRY(job_csv_init(j, A, 1));
+    const long long limit = max_steps < 0 ? (long long)INT_MAX : (long long)max_steps;  // :890
+    std::vector<double> frame_buf;
+    if (frame) frame_buf.resize((size_t)g.h * g.w);
+    long long launched = 0;
+    int chunk = frame ? 1 : 8;
+    bool all_done = false;
+    int pending = -1;  // state snapshot in flight (index into h_state halves)
+    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    while (launched < limit && !all_done) {
+        const int n = (int)std::min<long long>(chunk, limit - launched);
+        for (int s = 0; s < n; ++s) TRY(job_csv_launch_step(j, A, (int)((launched + s) & 1)));
+        launched += n;
+        // snapshot of the states after this chunk; wait for the PREVIOUS chunk's snapshot while this one runs
+        const int half = (pending + 1) & 1;
+        CU(c, cudaMemcpyAsync(j->h_state + (size_t)half * g.count, j->d_state, (size_t)g.count * sizeof(CsvState),
+                              cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaEventRecord(c->ev[2 + half], c->stream));
+        const int wait_half = frame ? half : (pending >= 0 ? pending : -1);
+        if (wait_half >= 0) {
+            CU(c, cudaEventSynchronize(c->ev[2 + wait_half]));
+            all_done = true;
+            for (int m = 0; m < g.count; ++m) all_done = all_done && j->h_state[(size_t)wait_half * g.count + m].done;
+        }
+        pending = half;
+        if (frame) {  // vwm.write_frame(u, "t = n"), src/main.cpp:997
+            const CsvState &st = j->h_state[(size_t)half * g.count];
+            const double *src = j->d_u[st.steps_done & 1] + (size_t)HALO * g.pitch;
+            CU(c, cudaMemcpy2DAsync(frame_buf.data(), g.w * sizeof(double), src, g.pitch * sizeof(double), g.w * sizeof(double),
+                                    g.h, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            c->stats.d2h_bytes += (uint64_t)g.h * g.w * sizeof(double);
+            if (frame(frame_buf.data(), g.h, g.w, st.steps_done, user) != 0)
+                return fail(c, CVB_ERR_CALLBACK, "frame observer aborted the run at step %d", st.steps_done);
+        }
+        chunk = frame ? 1 : std::min(chunk * 2, 64);
+    }
+    CU(c, cudaEventRecord(c->ev[1], c->stream));
+    TRY(job_fetch_state(j));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->stats.csv_ms += ms;
+    c->stats.d2h_bytes += (uint64_t)g.count * sizeof(CsvState);
+    for (int m = 0; m < g.count; ++m) {
+        if (steps_done) steps_done[m] = j->h_state[m].steps_done;
+        if (last_norm) last_norm[m] = j->h_state[m].norm;
+    }
+    return CVB_OK;
+}
+
+static cvb_status job_region_means(Job *j, double eps, double *c1, double *c2, int index) {
+    cvb_context *c = j->ctx;
+    if (!(eps > 0.0) || !c1 || !c2) return fail(c, CVB_ERR_INVALID_ARGUMENT, "bad region_means arguments");
+    CU(c, cudaSetDevice(c->device));
+    cvb_csv_params p{};
+    p.eps = eps;
+    CsvArgs A;
+    fill_args(j, &p, 0.0, A);
+    TRY(job_csv_init(j, A, 2));
+    TRY(job_fetch_state(j));
+    for (int k = 0; k < j->g.nch; ++k) {
+        c1[k] = j->h_state[index].c1[k];
+        c2[k] = j->h_state[index].c2[k];
+    }
+    return CVB_OK;
+}
+
+static cvb_status job_csv_step(Job *j, const cvb_csv_params *p, const double *c1, const double *c2, double *norm) {
+    cvb_context *c = j->ctx;
+    TRY(check_params(c, p));
+    if (j->g.count != 1) return fail(c, CVB_ERR_INVALID_ARGUMENT, "csv_step works on a single image");
+    CU(c, cudaSetDevice(c->device));
+    CsvArgs A;
+    fill_args(j, p, 0.0, A);
+    TRY(job_fetch_state(j));
+    const int before = j->h_state[0].steps_done;
+    if (A.multi_rank) TRY(exchange_halo(j, j->d_u[before & 1], sizeof(double), 1));
+    TRY(job_csv_init(j, A, 2));  // means of the current u (also refreshes sumI)
+    if (c1 && c2) {              // test hook: given means
+        CU(c, cudaMemcpyAsync(&j->d_state->c1[0], c1, sizeof(double) * j->g.nch, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(&j->d_state->c2[0], c2, sizeof(double) * j->g.nch, cudaMemcpyHostToDevice, c->stream));
+    }
+    // a single step must not be suppressed by a stale done flag / stop value
+    const int zero = 0;
+    const double neg = -1.0;
+    CU(c, cudaMemcpyAsync(&j->d_state->done, &zero, sizeof zero, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(&j->d_state->stop, &neg, sizeof neg, cudaMemcpyHostToDevice, c->stream));
+    TRY(job_csv_launch_step(j, A, before & 1));
+    TRY(job_fetch_state(j));
+    if (norm) *norm = j->h_state[0].norm;
+    return CVB_OK;
+}
+
+// ---- sessions --------------------------------------------------------------------------------------------------
+extern "C" cvb_status cvb_session_create_slab(cvb_context *c, int n, int h, int w, int row_lo, int row_hi,
+                                              cvb_precision prec, cvb_session **out) {
+    if (!c || !out) return CVB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cvb_session *s = new cvb_session;
+    cvb_status st = job_init(s, c, 1, n, h, w, row_lo, row_hi, true, prec);
+    if (st != CVB_OK) {
+        s->ctx = c;
+        job_free(s);
+        delete s;
+        return st;
+    }
+    // the slab must own exactly this rank's groups when a communicator exists
+    if (c->nranks > 1) {
+        const int per = NGROUPS / c->nranks;
+        if (s->group_lo < c->rank * per || s->group_hi > (c->rank + 1) * per) {
+            job_free(s);
+            delete s;
+            return fail(c, CVB_ERR_INVALID_ARGUMENT, "slab rows do not match rank %d of %d (use cvb_slab_partition)", c->rank, c->nranks);
+        }
+    }
+    *out = s;
+    return CVB_OK;
+}
+extern "C" cvb_status cvb_session_create(cvb_context *c, int n, int h, int w, cvb_precision prec, cvb_session **out) {
+    if (!c || !out) return CVB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cvb_session *s = new cvb_session;
+    cvb_status st = job_init(s, c, 1, n, h, w, 0, h, false, prec);
+    if (st != CVB_OK) {
+        s->ctx = c;
+        job_free(s);
+        delete s;
+        return st;
+    }
+    *out = s;
+    return CVB_OK;
+}
+extern "C" void cvb_session_destroy(cvb_session *s) {
+    if (!s) return;
+    job_free(s);
+    delete s;
+}
+extern "C" cvb_status cvb_session_upload_image(cvb_session *s, const uint8_t *const *planes) {
+    return s ? job_upload_image(s, planes) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_upload_levelset(cvb_session *s, const double *u) {
+    return s ? job_upload_levelset(s, 0, u) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_init_checkerboard(cvb_session *s) {
+    return s ? job_init_checkerboard(s) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_perona_malik(cvb_session *s, double K, double L, double T, int *steps) {
+    return s ? job_perona_malik(s, K, L, T, steps) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_csv_run(cvb_session *s, const cvb_csv_params *p, double tol, int max_steps,
+                                          int *steps_done, double *last_norm, cvb_frame_fn frame, void *user) {
+    return s ? job_csv_run(s, p, tol, max_steps, steps_done, last_norm, frame, user) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_csv_step(cvb_session *s, const cvb_csv_params *p, const double *c1, const double *c2,
+                                           double *norm) {
+    return s ? job_csv_step(s, p, c1, c2, norm) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_region_means(cvb_session *s, double eps, double *c1, double *c2) {
+    return s ? job_region_means(s, eps, c1, c2, 0) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_download_levelset(cvb_session *s, double *u) {
+    return s ? job_download_levelset(s, 0, u) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_download_image(cvb_session *s, uint8_t *const *planes) {
+    return s ? job_download_image(s, 0, s->g.nch, planes) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_mask(cvb_session *s, int invert, uint8_t *mask) {
+    return s ? job_mask(s, 0, invert, mask) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_save_image(cvb_session *s) { return s ? job_save_image(s) : CVB_ERR_INVALID_ARGUMENT; }
+extern "C" cvb_status cvb_session_restore_image(cvb_session *s) { return s ? job_restore_image(s) : CVB_ERR_INVALID_ARGUMENT; }
+extern "C" cvb_status cvb_session_release_scratch(cvb_session *s) {
+    if (!s) return CVB_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(s->ctx->stream);
+    job_release_pm(s);
+    return CVB_OK;
+}
+
+// ---- batches ---------------------------------------------------------------------------------------------------
+extern "C" cvb_status cvb_batch_create(cvb_context *c, int count, int n, int h, int w, cvb_precision prec, cvb_batch **out) {
+    if (!c || !out) return CVB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cvb_batch *b = new cvb_batch;
+    cvb_status st = job_init(b, c, count, n, h, w, 0, h, false, prec);
+    if (st != CVB_OK) {
+        b->ctx = c;
+        job_free(b);
+        delete b;
+        return st;
+    }
+    *out = b;
+    return CVB_OK;
+}
+extern "C" void cvb_batch_destroy(cvb_batch *b) {
+    if (!b) return;
+    job_free(b);
+    delete b;
+}
+extern "C" cvb_status cvb_batch_upload_images(cvb_batch *b, const uint8_t *const *planes) {
+    return b ? job_upload_image(b, planes) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_upload_levelset(cvb_batch *b, const double *u0) {
+    return b ? job_upload_levelset(b, -1, u0) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_init_checkerboard(cvb_batch *b) {
+    return b ? job_init_checkerboard(b) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_perona_malik(cvb_batch *b, double K, double L, double T, int *steps) {
+    return b ? job_perona_malik(b, K, L, T, steps) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_csv_run(cvb_batch *b, const cvb_csv_params *p, double tol, int max_steps, int *steps_done,
+                                        double *last_norm) {
+    return b ? job_csv_run(b, p, tol, max_steps, steps_done, last_norm, nullptr, nullptr) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_download_levelset(cvb_batch *b, int index, double *u) {
+    return b ? job_download_levelset(b, index, u) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_download_image(cvb_batch *b, int index, uint8_t *const *planes) {
+    if (!b || index < 0 || index >= b->g.count) return CVB_ERR_INVALID_ARGUMENT;
+    return job_download_image(b, index * b->g.nch, b->g.nch, planes);
+}
+extern "C" cvb_status cvb_batch_mask(cvb_batch *b, int index, int invert, uint8_t *mask) {
+    return b ? job_mask(b, index, invert, mask) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_save_images(cvb_batch *b) { return b ? job_save_image(b) : CVB_ERR_INVALID_ARGUMENT; }
+extern "C" cvb_status cvb_batch_restore_images(cvb_batch *b) { return b ? job_restore_image(b) : CVB_ERR_INVALID_ARGUMENT; }
+extern "C" cvb_status cvb_batch_release_scratch(cvb_batch *b) {
+    if (!b) return CVB_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(b->ctx->stream);
+    job_release_pm(b);
+    return CVB_OK;
+}
+
+// ---- one-shot calls on host buffers (the drop-in seams) ------------------------------------------------------
+struct SessionGuard {
+    cvb_session *s = nullptr;
+    ~SessionGuard() { cvb_session_destroy(s); }
+};
+
+extern "C" cvb_status cvb_perona_malik(cvb_context *c, const uint8_t *const *planes_in, int n, int h, int w, double K,
+                                       double L, double T, uint8_t *const *planes_out, int *steps) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    if (!planes_in || !planes_out) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes is NULL");
+    SessionGuard g;
+    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    TRY(cvb_session_upload_image(g.s, planes_in));
+    TRY(cvb_session_perona_malik(g.s, K, L, T, steps));
+    return cvb_session_download_image(g.s, planes_out);
+}
+
+extern "C" cvb_status cvb_csv_run(cvb_context *c, const uint8_t *const *planes, int n, int h, int w, double *u_inout,
+                                  const cvb_csv_params *params, double tol, int max_steps, int *steps_done,
+                                  double *last_norm, cvb_frame_fn frame, void *user) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    SessionGuard g;
+    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    TRY(cvb_session_upload_image(g.s, planes));
+    TRY(cvb_session_upload_levelset(g.s, u_inout));
+    TRY(cvb_session_csv_run(g.s, params, tol, max_steps, steps_done, last_norm, frame, user));
+    return cvb_session_download_levelset(g.s, u_inout);
+}
+
+extern "C" cvb_status cvb_segment(cvb_context *c, const uint8_t *const *planes, int n, int h, int w, double *u_inout,
+                                  int smooth, double K, double L, double T, uint8_t *const *planes_pm_out,
+                                  const cvb_csv_params *params, double tol, int max_steps, int *steps_done,
+                                  double *last_norm, int invert, uint8_t *mask_out) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    SessionGuard g;
+    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    TRY(cvb_session_upload_image(g.s, planes));
+    TRY(cvb_session_upload_levelset(g.s, u_inout));
+    if (smooth) {
+        TRY(cvb_session_perona_malik(g.s, K, L, T, nullptr));
+        if (planes_pm_out) TRY(cvb_session_download_image(g.s, planes_pm_out));
+    }
+    TRY(cvb_session_csv_run(g.s, params, tol, max_steps, steps_done, last_norm, nullptr, nullptr));
+    TRY(cvb_session_download_levelset(g.s, u_inout));
+    if (mask_out) TRY(cvb_session_mask(g.s, invert, mask_out));
+    return CVB_OK;
+}
+
+extern "C" cvb_status cvb_region_means(cvb_context *c, const uint8_t *const *planes, int n, int h, int w, const double *u,
+                                       double eps, double *c1, double *c2) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    SessionGuard g;
+    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    TRY(cvb_session_upload_image(g.s, planes));
+    TRY(cvb_session_upload_levelset(g.s, u));
+    return cvb_session_region_means(g.s, eps, c1, c2);
+}
+
+extern "C" cvb_status cvb_curvature(cvb_context *c, const double *u, int h, int w, double *kappa) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    if (!u || !kappa) return fail(c, CVB_ERR_INVALID_ARGUMENT, "u / kappa is NULL");
+    SessionGuard g;
+    TRY(cvb_session_create(c, 1, h, w, CVB_PRECISION_F64, &g.s));
+    Job *j = g.s;
+    TRY(cvb_session_upload_levelset(g.s, u));
+    CU(c, cudaMalloc(&j->d_aux, (size_t)j->g.plane_elems * sizeof(double)));
+    CsvArgs A;
+    fill_args(j, nullptr, 0.0, A);
+    CU(c, launch_csv_kappa(A, c->math == CVB_MATH_STRICT, c->stream));
+    c->stats.kernel_launches += 1;
+    CU(c, cudaMemcpy2DAsync(kappa, w * sizeof(double), j->d_aux + (size_t)HALO * j->g.pitch, j->g.pitch * sizeof(double),
+                            w * sizeof(double), h, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += (uint64_t)h * w * sizeof(double);
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
+}
+
+extern "C" cvb_status cvb_delta_map(cvb_context *c, double *data, size_t count, double eps) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    if (!data && count) return fail(c, CVB_ERR_INVALID_ARGUMENT, "data is NULL");
+    if (count == 0) return CVB_OK;
+    CU(c, cudaSetDevice(c->device));
+    double *d = nullptr;
+    CU(c, cudaMalloc(&d, count * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, data, count * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_delta_map(d, count, eps, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(data, d, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    c->stats.kernel_launches += 1;
+    c->stats.h2d_bytes += count * sizeof(double);
+    c->stats.d2h_bytes += count * sizeof(double);
+    CU(c, e);
+    return CVB_OK;
+}
+
+extern "C" cvb_status cvb_stop_condition(cvb_context *c, const uint8_t *const *planes, int n, int h, int w, double tol,
+                                         double *stop) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    if (!stop) return fail(c, CVB_ERR_INVALID_ARGUMENT, "stop is NULL");
+    SessionGuard g;
+    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    TRY(cvb_session_upload_image(g.s, planes));
+    Job *j = g.s;
+    cvb_csv_params p{};
+    p.eps = 1.0;
+    CsvArgs A;
+    fill_args(j, &p, tol, A);
+    TRY(job_csv_init(j, A, 1));
+    TRY(job_fetch_state(j));
+    *stop = j->h_state[0].stop;
+    return CVB_OK;
+}
+
+extern "C" cvb_status cvb_mask(cvb_context *c, const double *u, int h, int w, int invert, uint8_t *mask) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    SessionGuard g;
+    TRY(cvb_session_create(c, 1, h, w, CVB_PRECISION_F64, &g.s));
+    TRY(cvb_session_upload_levelset(g.s, u));
+    return cvb_session_mask(g.s, invert, mask);
+}

@@ -1,0 +1,93 @@
+// Shared definitions for the sm_100a kernels of chan_vese_b200.
+//
+// Data layout in HBM (library-owned):
+//   every plane (level set u, PM state, uint8 image channel) of every image of a job is stored as
+//   rows_alloc x pitch elements, rows_alloc = (row_hi - row_lo) + 2*HALO, local row 0 = global row
+//   row_lo - HALO.  pitch is a multiple of 16 elements, so a thread's two adjacent columns form one
+//   aligned 16-byte (fp64) access and every row starts on a 128-byte line.  Halo rows hold the
+//   neighbouring slab's rows (multi-GPU) and are unused at the global image border, where indices
+//   are clamped (BORDER_REPLICATE / clamped neighbours of the reference, src/main.cpp:351-354,
+//   527-530).  Planes of one kind are contiguous: plane (image m, channel k) = base + (m*nch+k)*plane_elems.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvb {
+
+constexpr int HALO = 2;            // halo rows above and below a slab (PM needs 2/2, CSV 2/1)
+constexpr int WARPS_PER_CTA = 4;   // a CTA = 4 warps = 4 adjacent column strips of one row segment
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int STRIP_LANES = 64;    // columns touched by a warp: each lane owns 2 adjacent columns
+constexpr int CSV_STRIP_OWN = 62;  // lane 0 is a halo lane (it supplies nx of the column to the left)
+constexpr int PM_STRIP_OWN = 60;   // lanes 0 and 31 are halo lanes (radius-2 stencil)
+constexpr int CSV_CB = WARPS_PER_CTA * CSV_STRIP_OWN;  // 248 columns per CTA
+constexpr int PM_CB = WARPS_PER_CTA * PM_STRIP_OWN;    // 240 columns per CTA
+constexpr int MAX_CH = 3;
+// Accumulator slots of the fused reductions.  a(u) = atan(u/eps)/pi = H(u) - 1/2 (src/main.cpp:188-194):
+//   [0] sum a   [1..3] sum I_k*a   [4] sum du^2 (step) or sum mean_k(I)^2 (init)   [5..7] sum I_k (init)
+constexpr int NACC = 8;
+constexpr int ACC_A = 0, ACC_IA = 1, ACC_SQ = 4, ACC_I = 5;
+constexpr int NGROUPS = 32;        // fixed row groups of the deterministic reduction tree
+
+// Geometry of one job (a batch of `count` equal images, each possibly a row slab).
+struct Geom {
+    int h, w;            // global image size
+    int row_lo, row_hi;  // owned global rows [row_lo, row_hi)
+    int pitch;           // elements per row (all planes use the same element pitch)
+    int rows_alloc;      // row_hi - row_lo + 2*HALO
+    int nch;             // channels
+    int count;           // images in the job
+    int seg_rows;        // rows per segment; segments start at global rows that are multiples of it
+    int nseg;            // segments in [row_lo, row_hi)
+    int seg0;            // global index of the first local segment (row_lo / seg_rows)
+    int nseg_global;     // segments of the whole image
+    int ncb_csv, ncb_pm; // column blocks (CTAs per segment)
+    long long plane_elems;  // rows_alloc * pitch
+};
+
+// Per-image state of a CSV run, living in device memory.
+struct CsvState {
+    double c1[MAX_CH];      // region means used by the next step (src/main.cpp:973-974)
+    double c2[MAX_CH];
+    double sumI[MAX_CH];    // sum of I_k over the image (exact integers), set by csv_init
+    double sums[NACC];      // last reduced sums
+    double norm;            // ||du||_2 of the last executed step (src/main.cpp:993)
+    double stop;            // tol * || mean_k I_k ||_2 (src/main.cpp:949-960), set by csv_init
+    int done;               // 1 once norm <= stop (src/main.cpp:1000)
+    int steps_done;         // executed steps; u^n lives in buffer n & 1
+    unsigned int final_ticket;
+    unsigned int group_ticket[NGROUPS];
+    int pad;
+};
+
+struct CsvArgs {
+    double *u[2];           // ping-pong level-set buffers, count planes each
+    const uint8_t *img;     // count * nch planes
+    CsvState *state;        // count
+    double *partials;       // [count][nseg][ncb][WARPS_PER_CTA][NACC]
+    double *group_sums;     // [NGROUPS][count][NACC]
+    double *kappa_out;      // MODE_KAPPA only
+    const double *atan_tab; // 34 entries, see math.cuh
+    double alpha, beta, gamma;  // mu*dt, (1/N)*dt, -nu*dt (src/main.cpp:985 as one addWeighted)
+    double eps;
+    double lambda1[MAX_CH], lambda2[MAX_CH];
+    double tol;
+    int multi_rank;         // 1: stop after the group sums; csv_finalize runs after the all-gather
+    int ngroups_local;      // non-empty groups owned by this rank
+    Geom g;
+};
+
+struct PmArgs {
+    const void *in;   // double* or uint8_t* (first step), count*nch planes
+    void *out;        // double* or uint8_t* (last step)
+    double K, L;
+    Geom g;
+};
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+// first / one-past-last global segment of reduction group grp
+__host__ __device__ inline int group_seg_begin(int grp, int nseg_global) {
+    return (int)(((long long)grp * nseg_global + NGROUPS - 1) / NGROUPS);
+}
+
+}  // namespace cvb

@@ -1,0 +1,411 @@
+// Chan-Sandberg-Vese level-set kernels for sm_100a.
+//
+// csv_step_kernel fuses one whole iteration of the reference's time-step loop (src/main.cpp:963-1001)
+// into a single pass over HBM: curvature (:342-375), data term (:299-312, :968-980), the addWeighted
+// combine (:985), the regularised delta (:204-210 through ParallelPixelFunction, :988-992), the norm
+// (:993), the update (:994) AND the sums that give the next step's region means c1/c2 (:255-281,
+// :973-974) of the updated level set.  Algorithmic traffic: read u 8 B + write u 8 B + N bytes of image
+// per pixel per step (the reference moves ~0.9 kB).
+//
+// Mapping: a warp marches down a strip of 64 columns, each lane owning two adjacent columns (one 16-byte
+// access); rows i-1, i, i+1 live in registers, west/east neighbours come from warp shuffles, ny(i-1)
+// is carried from the previous row.  Lane 0 is a halo lane (it supplies nx of the column left of the
+// strip), so a strip owns 62 columns and a 4-warp CTA 248.  Loads run a software pipeline: L2 prefetch
+// CSV_PF rows ahead, register prefetch CSV_D rows ahead.
+#include "common.cuh"
+#include "kernels.h"
+#include "math.cuh"
+#include "reduce.cuh"
+
+namespace cvb {
+
+#ifndef CSV_D
+#define CSV_D 2
+#endif
+#ifndef CSV_PF
+#define CSV_PF 8
+#endif
+
+enum { MODE_STEP = 0, MODE_KAPPA = 1 };
+
+template <int NCH, bool STRICT, int MODE>
+__global__ void __launch_bounds__(CTA_THREADS, 4) csv_step_kernel(const __grid_constant__ CsvArgs A) {
+    const Geom &G = A.g;
+    __shared__ double s_tab[ATAN_TAB_N];
+    __shared__ double s_red[NACC][CTA_THREADS];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bid = blockIdx.x;
+    const int cb = bid % G.ncb_csv;
+    bid /= G.ncb_csv;
+    const int seg = bid % G.nseg;
+    const int img = bid / G.nseg;
+    CsvState *st = A.state + img;
+    if (MODE == MODE_STEP && st->done) return;  // frozen image: the launch is a no-op (src/main.cpp:1000)
+    if (tid < ATAN_TAB_N) s_tab[tid] = A.atan_tab[tid];
+    __syncthreads();
+
+    const int par = st->steps_done & 1;
+    const double *__restrict__ uin = A.u[par] + (size_t)img * G.plane_elems;
+    double *__restrict__ uout = (MODE == MODE_KAPPA ? A.kappa_out : A.u[par ^ 1]) + (size_t)img * G.plane_elems;
+    const uint8_t *__restrict__ im = A.img + (size_t)img * G.nch * G.plane_elems;
+
+    const int gseg = G.seg0 + seg;
+    const int ra = max(gseg * G.seg_rows, G.row_lo);
+    const int rb = min((gseg + 1) * G.seg_rows, G.row_hi);
+    const int cs = cb * CSV_CB + warp * CSV_STRIP_OWN;
+    const int a = cs - 2 + 2 * lane;  // this lane's columns: a, a+1
+    const int w = G.w, h = G.h;
+    const bool colok = a >= 0 && a < G.pitch;
+    const bool e2ok = lane == 31 && a + 2 < G.pitch;
+
+    // ---- per-step coefficients
+    const double eps = A.eps;
+    const double inv_eps = 1.0 / eps;
+    // fast: du = (kappa*alpha' + sum_k (A_k I^2 + B_k I) + q0) / (eps^2 + u^2), everything pre-scaled by eps/pi
+    double cA[NCH], cB[NCH], q0 = 0.0, alphap = 0.0, eps2 = eps * eps;
+    double c1[NCH], c2[NCH];
+    if (MODE == MODE_STEP) {
+        const double kd = eps * CVB_INV_PI;
+        const double bk = A.beta * kd;
+        alphap = A.alpha * kd;
+        q0 = A.gamma * kd;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            c1[k] = st->c1[k];
+            c2[k] = st->c2[k];
+            const double l1 = A.lambda1[k], l2 = A.lambda2[k];
+            cA[k] = bk * (l2 - l1);
+            cB[k] = 2.0 * bk * (l1 * c1[k] - l2 * c2[k]);
+            q0 += bk * (l2 * c2[k] * c2[k] - l1 * c1[k] * c1[k]);
+        }
+    }
+
+    double acc[NACC];
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
+
+    if (cs < w) {
+        const int nk = rb - ra + 3;  // streamed rows ra-2 .. rb
+        double2 pq[CSV_D];
+        double pe[CSV_D];
+        unsigned int pI[CSV_D][NCH];
+        auto row_off = [&](int k) -> size_t {
+            int gr = ra - 2 + k;
+            gr = min(max(gr, 0), h - 1);  // BORDER_REPLICATE in i (src/main.cpp:352,354)
+            return (size_t)(gr - G.row_lo + HALO) * G.pitch;
+        };
+        auto issue = [&](int k, int j) {
+            pq[j] = make_double2(0.0, 0.0);
+            pe[j] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) pI[j][c] = 0u;
+            if (k < nk) {
+                const size_t off = row_off(k);
+                if (colok) pq[j] = __ldg(reinterpret_cast<const double2 *>(uin + off + a));
+                if (e2ok) pe[j] = __ldg(uin + off + a + 2);
+                if (MODE == MODE_STEP && k >= 3 && colok) {
+                    const size_t offi = (size_t)(ra - 3 + k - G.row_lo + HALO) * G.pitch + a;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c)
+                        pI[j][c] = __ldg(reinterpret_cast<const unsigned short *>(im + (size_t)c * G.plane_elems + offi));
+                }
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < CSV_D; ++j) issue(j, j);
+
+        double2 N = make_double2(0.0, 0.0), C = make_double2(0.0, 0.0);
+        double e2c = 0.0, nyp0 = 0.0, nyp1 = 0.0;
+#pragma unroll 1
+        for (int k0 = 0; k0 < nk; k0 += CSV_D) {
+#pragma unroll
+            for (int j = 0; j < CSV_D; ++j) {
+                const int k = k0 + j;
+                if (k < nk) {
+                    const double2 S = pq[j];
+                    const double e2s = pe[j];
+                    unsigned int Ib[NCH];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) Ib[c] = pI[j][c];
+                    issue(k + CSV_D, j);
+                    if (k + CSV_PF < nk) {
+                        const size_t off = row_off(k + CSV_PF);
+                        if (colok) prefetch_l2(uin + off + a);
+                        if (MODE == MODE_STEP && lane < 3 * NCH) {
+                            const int c = lane / 3, o = (lane % 3) * 31;
+                            prefetch_l2(im + (size_t)c * G.plane_elems +
+                                        (size_t)(ra - 3 + k + CSV_PF - G.row_lo + HALO) * G.pitch + max(cs, 0) + o);
+                        }
+                    }
+                    if (k >= 2) {
+                        const int i = ra - 3 + k;  // ny of row i; output row when k >= 3
+                        const double ny0 = normal_component<STRICT>(S.x - C.x, S.x - N.x);  // :352,354,367-368
+                        const double ny1 = normal_component<STRICT>(S.y - C.y, S.y - N.y);
+                        if (k >= 3) {
+                            const double Wn = __shfl_up_sync(0xffffffffu, C.y, 1);
+                            double E2 = __shfl_down_sync(0xffffffffu, C.x, 1);
+                            if (lane == 31) E2 = e2c;
+                            // BORDER_REPLICATE in j (:351,353)
+                            const double E0 = (a + 1 < w) ? C.y : C.x;
+                            const double E1 = (a + 2 < w) ? E2 : C.y;
+                            const double W0 = (a >= 1) ? Wn : C.x;
+                            const double nx0 = normal_component<STRICT>(E0 - C.x, E0 - W0);  // :351,353,365-366
+                            const double nx1 = normal_component<STRICT>(E1 - C.y, E1 - C.x);
+                            const double nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
+                            // backward differences with replicate on the normalised fields (:371-373)
+                            const double kx0 = (a >= 1) ? nx0 - nxw : 0.0;
+                            const double kx1 = nx1 - nx0;
+                            const double ky0 = (i >= 1) ? ny0 - nyp0 : 0.0;
+                            const double ky1 = (i >= 1) ? ny1 - nyp1 : 0.0;
+                            const double kap0 = kx0 + ky0, kap1 = kx1 + ky1;
+                            const size_t offo = (size_t)(i - G.row_lo + HALO) * G.pitch + a;
+                            if (MODE == MODE_KAPPA) {
+                                if (lane >= 1) {
+                                    if (a + 1 < w)
+                                        *reinterpret_cast<double2 *>(uout + offo) = make_double2(kap0, kap1);
+                                    else if (a < w)
+                                        uout[offo] = kap0;
+                                }
+                            } else {
+                                double I0[NCH], I1[NCH];
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c) {
+                                    I0[c] = u8_to_double(Ib[c] & 0xffu);
+                                    I1[c] = u8_to_double(Ib[c] >> 8);
+                                }
+                                double du0, du1;
+                                if (STRICT) {
+                                    double s0 = 0.0, s1 = 0.0;  // u_diff, :965, :977-979 serial in k
+#pragma unroll
+                                    for (int c = 0; c < NCH; ++c) {
+                                        double t = __dadd_rn(I0[c], -c1[c]);
+                                        const double vi0 = __dmul_rn(__dmul_rn(t, t), A.lambda1[c]);
+                                        t = __dadd_rn(I0[c], -c2[c]);
+                                        const double vo0 = __dmul_rn(__dmul_rn(t, t), A.lambda2[c]);
+                                        s0 = __dadd_rn(s0, __dadd_rn(-vi0, vo0));
+                                        t = __dadd_rn(I1[c], -c1[c]);
+                                        const double vi1 = __dmul_rn(__dmul_rn(t, t), A.lambda1[c]);
+                                        t = __dadd_rn(I1[c], -c2[c]);
+                                        const double vo1 = __dmul_rn(__dmul_rn(t, t), A.lambda2[c]);
+                                        s1 = __dadd_rn(s1, __dadd_rn(-vi1, vo1));
+                                    }
+                                    // :985 as one addWeighted, then delta (:204-210), multiply (:992)
+                                    const double d0 =
+                                        __dadd_rn(__dadd_rn(__dmul_rn(kap0, A.alpha), __dmul_rn(s0, A.beta)), A.gamma);
+                                    const double d1 =
+                                        __dadd_rn(__dadd_rn(__dmul_rn(kap1, A.alpha), __dmul_rn(s1, A.beta)), A.gamma);
+                                    const double e2 = __dmul_rn(eps, eps);
+                                    const double de0 =
+                                        __ddiv_rn(eps, __dmul_rn(CVB_PI, __dadd_rn(e2, __dmul_rn(C.x, C.x))));
+                                    const double de1 =
+                                        __ddiv_rn(eps, __dmul_rn(CVB_PI, __dadd_rn(e2, __dmul_rn(C.y, C.y))));
+                                    du0 = __dmul_rn(d0, de0);
+                                    du1 = __dmul_rn(d1, de1);
+                                } else {
+                                    double t0 = q0, t1 = q0;
+#pragma unroll
+                                    for (int c = 0; c < NCH; ++c) {
+                                        t0 = fma(fma(cA[c], I0[c], cB[c]), I0[c], t0);
+                                        t1 = fma(fma(cA[c], I1[c], cB[c]), I1[c], t1);
+                                    }
+                                    t0 = fma(kap0, alphap, t0);
+                                    t1 = fma(kap1, alphap, t1);
+                                    du0 = t0 * fast_rcp(fma(C.x, C.x, eps2));
+                                    du1 = t1 * fast_rcp(fma(C.y, C.y, eps2));
+                                }
+                                const double un0 = __dadd_rn(C.x, du0), un1 = __dadd_rn(C.y, du1);  // :994
+                                const bool v0 = lane >= 1 && a < w, v1 = lane >= 1 && a + 1 < w;
+                                if (v1)
+                                    *reinterpret_cast<double2 *>(uout + offo) = make_double2(un0, un1);
+                                else if (v0)
+                                    uout[offo] = un0;
+                                // sums of the UPDATED level set (next step's c1/c2) and of du^2 (:993)
+                                double a0 = atan_over_pi(un0 * inv_eps, s_tab);
+                                double a1 = atan_over_pi(un1 * inv_eps, s_tab);
+                                a0 = v0 ? a0 : 0.0;
+                                a1 = v1 ? a1 : 0.0;
+                                du0 = v0 ? du0 : 0.0;
+                                du1 = v1 ? du1 : 0.0;
+                                acc[ACC_A] += a0;
+                                acc[ACC_A] += a1;
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c) {
+                                    acc[ACC_IA + c] = fma(I0[c], a0, acc[ACC_IA + c]);
+                                    acc[ACC_IA + c] = fma(I1[c], a1, acc[ACC_IA + c]);
+                                }
+                                acc[ACC_SQ] = fma(du0, du0, acc[ACC_SQ]);
+                                acc[ACC_SQ] = fma(du1, du1, acc[ACC_SQ]);
+                            }
+                        }
+                        nyp0 = ny0;
+                        nyp1 = ny1;
+                    }
+                    N = C;
+                    C = S;
+                    e2c = e2s;
+                }
+            }
+        }
+    }
+    if (MODE == MODE_STEP) finish_tile<NCH, false>(A, img, seg, cb, G.ncb_csv, acc, s_red, &s_flag, 0);
+}
+
+// Sums of the CURRENT level set and of the image: sum a, sum I_k*a, sum I_k, sum mean_k(I)^2.
+// Gives the first step's c1/c2 (src/main.cpp:973-974) and the stop condition (:949-960).
+template <int NCH>
+__global__ void __launch_bounds__(CTA_THREADS, 4) csv_init_kernel(const __grid_constant__ CsvArgs A, int final_mode) {
+    const Geom &G = A.g;
+    __shared__ double s_tab[ATAN_TAB_N];
+    __shared__ double s_red[NACC][CTA_THREADS];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bid = blockIdx.x;
+    const int cb = bid % G.ncb_csv;
+    bid /= G.ncb_csv;
+    const int seg = bid % G.nseg;
+    const int img = bid / G.nseg;
+    CsvState *st = A.state + img;
+    if (tid < ATAN_TAB_N) s_tab[tid] = A.atan_tab[tid];
+    __syncthreads();
+    const int par = (final_mode == 1) ? 0 : (st->steps_done & 1);
+    const double *__restrict__ uin = A.u[par] + (size_t)img * G.plane_elems;
+    const uint8_t *__restrict__ im = A.img + (size_t)img * G.nch * G.plane_elems;
+    const int gseg = G.seg0 + seg;
+    const int ra = max(gseg * G.seg_rows, G.row_lo);
+    const int rb = min((gseg + 1) * G.seg_rows, G.row_hi);
+    const int cs = cb * CSV_CB + warp * CSV_STRIP_OWN;
+    const int a = cs - 2 + 2 * lane;
+    const int w = G.w;
+    const double inv_eps = 1.0 / A.eps;
+    const double inv_n = 1.0 / (double)NCH;  // Mat /= N multiplies by 1/N (src/main.cpp:958)
+    double acc[NACC];
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
+    if (lane >= 1 && a < w) {
+        const bool v1 = a + 1 < w;
+        for (int i = ra; i < rb; ++i) {
+            const size_t off = (size_t)(i - G.row_lo + HALO) * G.pitch + a;
+            const double2 U = __ldg(reinterpret_cast<const double2 *>(uin + off));
+            double a0 = atan_over_pi(U.x * inv_eps, s_tab);
+            double a1 = atan_over_pi(U.y * inv_eps, s_tab);
+            a1 = v1 ? a1 : 0.0;
+            acc[ACC_A] += a0;
+            acc[ACC_A] += a1;
+            double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const unsigned int b = __ldg(reinterpret_cast<const unsigned short *>(im + (size_t)c * G.plane_elems + off));
+                const double I0 = u8_to_double(b & 0xffu);
+                const double I1 = v1 ? u8_to_double(b >> 8) : 0.0;
+                acc[ACC_IA + c] = fma(I0, a0, acc[ACC_IA + c]);
+                acc[ACC_IA + c] = fma(I1, a1, acc[ACC_IA + c]);
+                acc[ACC_I + c] += I0;
+                acc[ACC_I + c] += I1;
+                m0 += I0;
+                m1 += I1;
+            }
+            m0 *= inv_n;
+            m1 *= inv_n;
+            acc[ACC_SQ] = fma(m0, m0, acc[ACC_SQ]);
+            acc[ACC_SQ] = fma(m1, m1, acc[ACC_SQ]);
+        }
+    }
+    finish_tile<NCH, true>(A, img, seg, cb, G.ncb_csv, acc, s_red, &s_flag, final_mode);
+}
+
+// Multi-rank path: after the all-gather of the group sums, one thread per image.
+__global__ void csv_finalize_kernel(const __grid_constant__ CsvArgs A, int mode) {
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= A.g.count) return;
+    if (mode == 0 && A.state[img].done) return;
+    csv_finalize_image(A, img, mode);
+}
+
+// ---- elementwise helpers ------------------------------------------------------------------------------
+// ParallelPixelFunction with f = regularized_delta (src/ParallelPixelFunction.cpp:12-17, main.cpp:204-210,989)
+__global__ void delta_map_kernel(double *data, size_t n, double eps) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const double e2 = __dmul_rn(eps, eps);
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+        const double x = data[q];
+        data[q] = __ddiv_rn(eps, __dmul_rn(CVB_PI, __dadd_rn(e2, __dmul_rn(x, x))));
+    }
+}
+
+// separate()'s mask: float32(u) > 0, optionally inverted (src/main.cpp:395-400).  Pitched in, pitched out.
+__global__ void mask_kernel(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= w || i >= rows) return;
+    const size_t q = (size_t)i * pitch + j;
+    const uint8_t m = (__double2float_rn(u[q]) > 0.0f) ? 1 : 0;
+    mask[q] = invert ? (uint8_t)(1 - m) : m;
+}
+
+// u0(i,j) = si[i] * sj[j] with host-computed sign vectors (bit parity with glibc sin)
+__global__ void checkerboard_kernel(double *u, const signed char *si, const signed char *sj, int row_lo, int rows,
+                                    int w, int pitch) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= w || i >= rows) return;
+    u[(size_t)(i + HALO) * pitch + j] = (double)((int)si[row_lo + i] * (int)sj[j]);
+}
+
+// ---- host launchers -----------------------------------------------------------------------------------
+template <int NCH>
+static cudaError_t launch_step_n(const CsvArgs &A, bool strict, int mode, cudaStream_t s) {
+    const Geom &G = A.g;
+    const unsigned int grid = (unsigned int)((size_t)G.count * G.nseg * G.ncb_csv);
+    if (mode == MODE_KAPPA) {
+        if (strict)
+            csv_step_kernel<NCH, true, MODE_KAPPA><<<grid, CTA_THREADS, 0, s>>>(A);
+        else
+            csv_step_kernel<NCH, false, MODE_KAPPA><<<grid, CTA_THREADS, 0, s>>>(A);
+    } else {
+        if (strict)
+            csv_step_kernel<NCH, true, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
+        else
+            csv_step_kernel<NCH, false, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_csv_step(const CsvArgs &A, bool strict, cudaStream_t s) {
+    return A.g.nch == 1 ? launch_step_n<1>(A, strict, MODE_STEP, s) : launch_step_n<3>(A, strict, MODE_STEP, s);
+}
+cudaError_t launch_csv_kappa(const CsvArgs &A, bool strict, cudaStream_t s) {
+    return launch_step_n<1>(A, strict, MODE_KAPPA, s);
+}
+cudaError_t launch_csv_init(const CsvArgs &A, int final_mode, cudaStream_t s) {
+    const Geom &G = A.g;
+    const unsigned int grid = (unsigned int)((size_t)G.count * G.nseg * G.ncb_csv);
+    if (G.nch == 1)
+        csv_init_kernel<1><<<grid, CTA_THREADS, 0, s>>>(A, final_mode);
+    else
+        csv_init_kernel<3><<<grid, CTA_THREADS, 0, s>>>(A, final_mode);
+    return cudaGetLastError();
+}
+cudaError_t launch_csv_finalize(const CsvArgs &A, int mode, cudaStream_t s) {
+    csv_finalize_kernel<<<(A.g.count + 127) / 128, 128, 0, s>>>(A, mode);
+    return cudaGetLastError();
+}
+cudaError_t launch_delta_map(double *data, size_t n, double eps, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const unsigned int grid = (unsigned int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    delta_map_kernel<<<grid, 256, 0, s>>>(data, n, eps);
+    return cudaGetLastError();
+}
+cudaError_t launch_mask(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s) {
+    dim3 grid((w + 255) / 256, rows);
+    mask_kernel<<<grid, 256, 0, s>>>(u, mask, rows, w, pitch, invert);
+    return cudaGetLastError();
+}
+cudaError_t launch_checkerboard(double *u, const signed char *si, const signed char *sj, int row_lo, int rows, int w,
+                                int pitch, cudaStream_t s) {
+    dim3 grid((w + 255) / 256, rows);
+    checkerboard_kernel<<<grid, 256, 0, s>>>(u, si, sj, row_lo, rows, w, pitch);
+    return cudaGetLastError();
+}
+
+}  // namespace cvb

@@ -1,0 +1,25 @@
+// Host-side launchers of the sm_100a kernels (definitions in csv_kernels.cu / pm_kernels.cu).
+#pragma once
+#include <algorithm>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace cvb {
+
+cudaError_t launch_csv_step(const CsvArgs &A, bool strict, cudaStream_t s);
+cudaError_t launch_csv_kappa(const CsvArgs &A, bool strict, cudaStream_t s);
+// final_mode 1: reset counters + stop condition; 2: region means only
+cudaError_t launch_csv_init(const CsvArgs &A, int final_mode, cudaStream_t s);
+cudaError_t launch_csv_finalize(const CsvArgs &A, int mode, cudaStream_t s);
+cudaError_t launch_delta_map(double *data, size_t n, double eps, cudaStream_t s);
+cudaError_t launch_mask(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s);
+cudaError_t launch_checkerboard(double *u, const signed char *si, const signed char *sj, int row_lo, int rows, int w,
+                                int pitch, cudaStream_t s);
+
+// in_u8 / out_u8: the first step reads the uint8 image, the last one writes it (fused quantisation)
+cudaError_t launch_pm_step(const PmArgs &A, bool in_u8, bool out_u8, bool strict, cudaStream_t s);
+cudaError_t launch_pm_quantise(const double *in, uint8_t *out, size_t n, cudaStream_t s);
+
+}  // namespace cvb

@@ -1,0 +1,102 @@
+// Device math for the fp64 solvers.
+//
+// The fused CSV step is bound by the FP64 pipe (64 lanes/clk/SM on B200), not by HBM, once the HBM
+// traffic is down to 16+N bytes/pixel, so the production ("fast") math counts FP64 instructions:
+//   * reciprocal / rsqrt = MUFU seed (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64) + ONE cubic
+//     Newton step (3 resp. 5 DFMA-class ops, ~1 ulp), no IEEE division or sqrt sequences;
+//   * atan(x)/pi by a 32-interval table-driven argument reduction with one reciprocal and a degree-5
+//     polynomial (17 FP64 ops, <= 4 ulp; the CUDA libm atan is ~2x that);
+//   * uint8 -> double through the 2^52 magic constant (1 DADD instead of a quarter-rate I2F.F64).
+// "Strict" math reproduces the oracle's operation order with IEEE div/sqrt and no FMA contraction
+// (the reference build has no FMA and forbids reassociation, Makefile:16): a test mode.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvb {
+
+#define CVB_PI 3.14159265358979323846
+#define CVB_INV_PI 0.31830988618379067154
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ double rcp_seed(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double rsqrt_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+// 1/x for normal positive x: seed (>= 20 bits) + cubic step, 3 FP64 ops
+__device__ __forceinline__ double fast_rcp(double x) {
+    const double y = rcp_seed(x);
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    return fma(y, e, y);
+}
+// 1/sqrt(x) for normal positive x: seed + cubic step, 5 FP64 ops
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    const double y = rsqrt_seed(x);
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
+}
+
+// uint8 -> double, exact: bits(2^52 + v) - 2^52
+__device__ __forceinline__ double u8_to_double(unsigned int v) {
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+
+// ---- atan(x)/pi ------------------------------------------------------------------------------------
+// t = |x|.  t < 2^-4: c = 0.  2^-4 <= t < 2^4: c = centre of t's quarter-octave (exponent and top two
+// mantissa bits of t kept, third bit set).  atan t = atan c + atan z, z = (t-c)/(1+t*c), |z| <= 1/16.
+// t >= 2^4: atan t = pi/2 + atan(-1/t).  tab[0] = 0, tab[1+q] = atan(c_q)/pi (q = 0..31), tab[33] = 1/2.
+constexpr int ATAN_TAB_N = 34;
+constexpr int ATAN_Q0 = 1019 * 4;  // (biased exponent of 2^-4) * 4
+
+__device__ __forceinline__ double atan_over_pi(double x, const double *tab /* shared memory */) {
+    const int hx = __double2hiint(x);
+    const int ht = hx & 0x7fffffff;
+    const double t = __hiloint2double(ht, __double2loint(x));
+    const int q = (ht >> 18) - ATAN_Q0;
+    const bool big = q >= 32;
+    const bool mid = q >= 0 && !big;
+    const double c = __hiloint2double(mid ? ((ht & 0xfffc0000) | 0x00020000) : 0, 0);
+    const int idx = min(max(q + 1, 0), 33);
+    const double hi = tab[idx];
+    const double num = big ? -1.0 : t - c;
+    const double den = big ? t : fma(t, c, 1.0);
+    const double z = num * fast_rcp(den);
+    const double w = z * z;
+    double p = fma(w, 1.0 / 13.0, -1.0 / 11.0);
+    p = fma(p, w, 1.0 / 9.0);
+    p = fma(p, w, -1.0 / 7.0);
+    p = fma(p, w, 1.0 / 5.0);
+    p = fma(p, w, -1.0 / 3.0);
+    const double zw = z * w;
+    const double at = fma(zw, p, z);          // atan z
+    const double r = fma(at, CVB_INV_PI, hi);  // >= 0
+    return __hiloint2double(__double2hiint(r) | (hx & 0x80000000), __double2loint(r));
+}
+
+// ---- curvature normal component n = up / sqrt(up^2 + uc^2 + eta^2), src/main.cpp:365-368 --------------
+// d = E - W (so uc = d/2, uc^2 = d^2/4 exactly)
+template <bool STRICT>
+__device__ __forceinline__ double normal_component(double up, double d) {
+    if (STRICT) {
+        const double uc = __dmul_rn(0.5, d);
+        const double s = __dadd_rn(__dadd_rn(__dmul_rn(up, up), __dmul_rn(uc, uc)), 1e-8 * 1e-8);
+        return __ddiv_rn(up, __dsqrt_rn(s));
+    } else {
+        double s = fma(up, up, 1e-16);
+        s = fma(d * d, 0.25, s);
+        return up * fast_rsqrt(s);
+    }
+}
+
+}  // namespace cvb

@@ -1,0 +1,215 @@
+// Perona-Malik anisotropic diffusion kernels for sm_100a.
+//
+// pm_step_kernel fuses one iteration of the reference's diffusion loop (src/main.cpp:498-552): the two
+// Sobel passes (:503-504), the edge-stopping function g (:513-522) and the 4-neighbour flux update
+// (:524-548) in a single pass over HBM -- read I 8 B, write I' 8 B per channel-pixel (the reference makes
+// ~9 full-array passes).  The first step reads the uint8 image directly, the last one rounds to uint8
+// (saturate_cast, :551), so no separate conversion passes exist.
+//
+// Mapping: as in csv_kernels.cu a warp marches down a strip of 64 columns, two per lane.  Rows i-1..i+2
+// of I, three rows of the separable Sobel row sums and three rows of g live in registers; west/east
+// neighbours come from warp shuffles.  The stencil has radius 2, so lanes 0 and 31 are halo lanes:
+// a strip owns 60 columns, a 4-warp CTA 240.
+#include "common.cuh"
+#include "kernels.h"
+#include "math.cuh"
+
+namespace cvb {
+
+#ifndef PM_D
+#define PM_D 2
+#endif
+#ifndef PM_PF
+#define PM_PF 8
+#endif
+
+template <typename T>
+__device__ __forceinline__ double2 pm_load2(const T *p);
+template <>
+__device__ __forceinline__ double2 pm_load2<double>(const double *p) {
+    return __ldg(reinterpret_cast<const double2 *>(p));
+}
+template <>
+__device__ __forceinline__ double2 pm_load2<uint8_t>(const uint8_t *p) {  // :495-496 uint8 -> fp64
+    const unsigned int b = __ldg(reinterpret_cast<const unsigned short *>(p));
+    return make_double2(u8_to_double(b & 0xffu), u8_to_double(b >> 8));
+}
+// saturate_cast<uchar>(double): cvRound (round-half-even) then clamp, src/main.cpp:551
+__device__ __forceinline__ unsigned int sat_u8(double v) {
+    const int r = __double2int_rn(v);
+    return (unsigned int)min(max(r, 0), 255);
+}
+__device__ __forceinline__ void pm_store(double *p, double x, double y, bool two) {
+    if (two)
+        *reinterpret_cast<double2 *>(p) = make_double2(x, y);
+    else
+        *p = x;
+}
+__device__ __forceinline__ void pm_store(uint8_t *p, double x, double y, bool two) {
+    if (two)
+        *reinterpret_cast<unsigned short *>(p) = (unsigned short)(sat_u8(x) | (sat_u8(y) << 8));
+    else
+        *p = (uint8_t)sat_u8(x);
+}
+
+// g = 1 / (1 + (gx^2 + gy^2) / K^2), src/main.cpp:518-521
+template <bool STRICT>
+__device__ __forceinline__ double edge_stop(double gx, double gy, double K, double inv_k2) {
+    if (STRICT) {
+        const double mag = __dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy));
+        return __ddiv_rn(1.0, __dadd_rn(1.0, __ddiv_rn(mag, __dmul_rn(K, K))));
+    } else {
+        const double mag = fma(gx, gx, gy * gy);
+        return fast_rcp(fma(mag, inv_k2, 1.0));
+    }
+}
+// I0 + L*((gS+g0)(IS-I0) + (gE+g0)(IE-I0) + (gN+g0)(IN-I0) + (gW+g0)(IW-I0))/4, src/main.cpp:544-547
+template <bool STRICT>
+__device__ __forceinline__ double pm_update(double I0, double IS, double IE, double IN, double IW, double g0,
+                                            double gS, double gE, double gN, double gW, double L, double lq) {
+    if (STRICT) {
+        double s = __dmul_rn(__dadd_rn(gS, g0), __dadd_rn(IS, -I0));
+        s = __dadd_rn(s, __dmul_rn(__dadd_rn(gE, g0), __dadd_rn(IE, -I0)));
+        s = __dadd_rn(s, __dmul_rn(__dadd_rn(gN, g0), __dadd_rn(IN, -I0)));
+        s = __dadd_rn(s, __dmul_rn(__dadd_rn(gW, g0), __dadd_rn(IW, -I0)));
+        return __dadd_rn(I0, __ddiv_rn(__dmul_rn(L, s), 4.0));
+    } else {
+        double s = (gS + g0) * (IS - I0);
+        s = fma(gE + g0, IE - I0, s);
+        s = fma(gN + g0, IN - I0, s);
+        s = fma(gW + g0, IW - I0, s);
+        return fma(s, lq, I0);
+    }
+}
+
+template <typename TIN, typename TOUT, bool STRICT>
+__global__ void __launch_bounds__(CTA_THREADS, 4) pm_step_kernel(const __grid_constant__ PmArgs A) {
+    const Geom &G = A.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int bid = blockIdx.x;
+    const int cb = bid % G.ncb_pm;
+    bid /= G.ncb_pm;
+    const int seg = bid % G.nseg;
+    const int plane = bid / G.nseg;  // image * nch + channel: channels diffuse independently (:489)
+    const TIN *__restrict__ in = reinterpret_cast<const TIN *>(A.in) + (size_t)plane * G.plane_elems;
+    TOUT *__restrict__ out = reinterpret_cast<TOUT *>(A.out) + (size_t)plane * G.plane_elems;
+    const int gseg = G.seg0 + seg;
+    const int ra = max(gseg * G.seg_rows, G.row_lo);
+    const int rb = min((gseg + 1) * G.seg_rows, G.row_hi);
+    const int cs = cb * PM_CB + warp * PM_STRIP_OWN;
+    if (cs >= G.w) return;
+    const int a = cs - 2 + 2 * lane;
+    const int w = G.w, h = G.h;
+    const bool colok = a >= 0 && a < G.pitch;
+    const double K = A.K, L = A.L;
+    const double inv_k2 = 1.0 / (K * K), lq = L * 0.25;
+
+    const int nk = rb - ra + 4;  // streamed rows ra-2 .. rb+1
+    auto row_off = [&](int k) -> size_t {
+        int gr = ra - 2 + k;
+        gr = min(max(gr, 0), h - 1);  // clamped neighbours in i (:527-528)
+        return (size_t)(gr - G.row_lo + HALO) * G.pitch;
+    };
+    double2 pq[PM_D];
+    auto issue = [&](int k, int j) {
+        pq[j] = make_double2(0.0, 0.0);
+        if (k < nk && colok) pq[j] = pm_load2<TIN>(in + row_off(k) + a);
+    };
+#pragma unroll
+    for (int j = 0; j < PM_D; ++j) issue(j, j);
+
+    const double2 z2 = make_double2(0.0, 0.0);
+    double2 IN = z2, IC = z2, IS = z2;     // rows r-3, r-2, r-1 of I
+    double2 rdA = z2, rdB = z2, rsA = z2, rsB = z2;  // Sobel row sums of rows r-2, r-1
+    double2 gN = z2, gC = z2;              // g of rows r-3, r-2
+    const bool bc0 = (a == 0) || (a == w - 1), bc1 = (a + 1 == w - 1);  // border columns (:516)
+#pragma unroll 1
+    for (int k0 = 0; k0 < nk; k0 += PM_D) {
+#pragma unroll
+        for (int j = 0; j < PM_D; ++j) {
+            const int k = k0 + j;
+            if (k < nk) {
+                const double2 X = pq[j];  // row r = ra-2+k
+                issue(k + PM_D, j);
+                if (k + PM_PF < nk && colok) prefetch_l2(in + row_off(k + PM_PF) + a);
+                // separable 3x3 Sobel, row pass (summation order of cv2: (l + 2c) + r, r - l)
+                const double Wn = __shfl_up_sync(0xffffffffu, X.y, 1);
+                const double E2 = __shfl_down_sync(0xffffffffu, X.x, 1);
+                double2 rdC, rsC;
+                rdC.x = X.y - Wn;
+                rsC.x = __dadd_rn(fma(2.0, X.x, Wn), X.y);
+                rdC.y = E2 - X.x;
+                rsC.y = __dadd_rn(fma(2.0, X.y, X.x), E2);
+                double2 gS = z2;
+                if (k >= 2) {
+                    // g of row r-1: column pass 2*m + (t + b), b - t, then :513-522
+                    const int ig = ra - 3 + k;
+                    const double gx0 = fma(2.0, rdB.x, __dadd_rn(rdA.x, rdC.x));
+                    const double gx1 = fma(2.0, rdB.y, __dadd_rn(rdA.y, rdC.y));
+                    const double gy0 = rsC.x - rsA.x, gy1 = rsC.y - rsA.y;
+                    gS.x = edge_stop<STRICT>(gx0, gy0, K, inv_k2);
+                    gS.y = edge_stop<STRICT>(gx1, gy1, K, inv_k2);
+                    const bool br = (ig == 0) || (ig == h - 1);
+                    if (br || bc0) gS.x = 1.0;
+                    if (br || bc1) gS.y = 1.0;
+                }
+                if (k >= 4) {
+                    const int i = ra - 4 + k;  // output row: I rows IN, IC, IS = i-1, i, i+1
+                    const double Wc = __shfl_up_sync(0xffffffffu, IC.y, 1);
+                    const double Ec = __shfl_down_sync(0xffffffffu, IC.x, 1);
+                    const double gW = __shfl_up_sync(0xffffffffu, gC.y, 1);
+                    const double gE = __shfl_down_sync(0xffffffffu, gC.x, 1);
+                    // clamped neighbours in j (:529-530): a clamped neighbour is the pixel itself
+                    const bool w0 = a >= 1, e0 = a + 1 < w, e1 = a + 2 < w;
+                    const double o0 = pm_update<STRICT>(IC.x, IS.x, e0 ? IC.y : IC.x, IN.x, w0 ? Wc : IC.x, gC.x, gS.x,
+                                                        e0 ? gC.y : gC.x, gN.x, w0 ? gW : gC.x, L, lq);
+                    const double o1 = pm_update<STRICT>(IC.y, IS.y, e1 ? Ec : IC.y, IN.y, IC.x, gC.y, gS.y,
+                                                        e1 ? gE : gC.y, gN.y, gC.x, L, lq);
+                    if (lane >= 1 && lane <= 30 && a < w)
+                        pm_store(out + (size_t)(i - G.row_lo + HALO) * G.pitch + a, o0, o1, a + 1 < w);
+                }
+                IN = IC;
+                IC = IS;
+                IS = X;
+                rdA = rdB;
+                rdB = rdC;
+                rsA = rsB;
+                rsB = rsC;
+                gN = gC;
+                gC = gS;
+            }
+        }
+    }
+}
+
+__global__ void pm_quantise_kernel(const double *in, uint8_t *out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) out[q] = (uint8_t)sat_u8(in[q]);
+}
+
+template <typename TIN, typename TOUT>
+static cudaError_t launch_pm_t(const PmArgs &A, bool strict, cudaStream_t s) {
+    const Geom &G = A.g;
+    const unsigned int grid = (unsigned int)((size_t)G.count * G.nch * G.nseg * G.ncb_pm);
+    if (strict)
+        pm_step_kernel<TIN, TOUT, true><<<grid, CTA_THREADS, 0, s>>>(A);
+    else
+        pm_step_kernel<TIN, TOUT, false><<<grid, CTA_THREADS, 0, s>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pm_step(const PmArgs &A, bool in_u8, bool out_u8, bool strict, cudaStream_t s) {
+    if (in_u8 && out_u8) return launch_pm_t<uint8_t, uint8_t>(A, strict, s);
+    if (in_u8) return launch_pm_t<uint8_t, double>(A, strict, s);
+    if (out_u8) return launch_pm_t<double, uint8_t>(A, strict, s);
+    return launch_pm_t<double, double>(A, strict, s);
+}
+
+cudaError_t launch_pm_quantise(const double *in, uint8_t *out, size_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const unsigned int grid = (unsigned int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    pm_quantise_kernel<<<grid, 256, 0, s>>>(in, out, n);
+    return cudaGetLastError();
+}
+
+}  // namespace cvb

@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star: "level-set function in fp64 within a stated relative tolerance ... final
+segmentation mask with >= 99.9 % pixel agreement"):
+  * strict math, one step with given region means: BIT-EXACT level set (the arithmetic is the reference's);
+  * fast math (production): rel-L2(u) <= 1e-6 after full runs (measured ~1e-9), identical step
+    counts, mask agreement 100 % on the fixtures (>= 99.9 % required);
+  * PM uint8 planes: bit-exact in strict mode; fast mode >= 99.99 % equal and |delta| <= 1 (ties at x.5).
+"""
+import numpy as np
+import pytest
+
+import chan_vese_b200 as cv
+from chan_vese_b200 import synth
+from conftest import SMALL, rel_l2
+from oracle import coracle as co
+
+pytestmark = pytest.mark.gpu
+
+TOL_U = 1e-6
+
+
+def _p(kat, name, n, mk):
+    v = kat[name + "_params"]
+    return mk(v[0], v[1], v[2], v[3], list(v[4:4 + n]), list(v[7:7 + n]), nch=n)
+
+
+def _planes_close(a, b, frac=0.9999):
+    a, b = np.stack(a).astype(np.int16), np.stack(b).astype(np.int16)
+    assert np.abs(a - b).max() <= 1
+    assert (a == b).mean() >= frac
+
+
+@pytest.fixture()
+def strict(ctx):
+    ctx.set_math_mode(True)
+    yield ctx
+    ctx.set_math_mode(False)
+
+
+# ---- single kernels ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SMALL)
+def test_curvature(ctx, kat, name):
+    u = kat[name + "_u"]
+    k = ctx.curvature(u)
+    np.testing.assert_allclose(k, kat[name + "_kappa"], rtol=0, atol=2e-14)
+    ctx.set_math_mode(True)
+    try:
+        assert np.array_equal(ctx.curvature(u), kat[name + "_kappa"])  # bit-exact with cv::filter2D arithmetic
+    finally:
+        ctx.set_math_mode(False)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_region_means_stop_mask(ctx, kat, name):
+    img = list(kat[name + "_img"])
+    u = kat[name + "_u"]
+    c1, c2 = ctx.region_means(img, u, 1.0)
+    np.testing.assert_allclose(c1, kat[name + "_c1"], rtol=1e-12)
+    np.testing.assert_allclose(c2, kat[name + "_c2"], rtol=1e-12)
+    assert abs(ctx.stop_condition(img, 1e-3) - kat[name + "_stop"]) <= 1e-13 * kat[name + "_stop"]
+    assert np.array_equal(ctx.mask(u), kat[name + "_mask"])
+    assert np.array_equal(ctx.mask(u, True), 1 - kat[name + "_mask"])
+    h, w = u.shape
+    assert cv.region_variance(img[0], u, h, w, cv.Region.Inside, ctx=ctx) == pytest.approx(kat[name + "_c1"][0], rel=1e-12)
+    assert cv.region_variance(img[0], u, h, w, cv.Region.Outside, ctx=ctx) == pytest.approx(kat[name + "_c2"][0], rel=1e-12)
+
+
+def test_delta_map_parallel_pixel_function(ctx, kat):
+    xs = np.ascontiguousarray(kat["hd_x"])
+    d = xs.copy()
+    ctx.delta_map(d, 0.7)
+    assert np.array_equal(d, kat["delta"])  # IEEE div/mul/add in the reference's order
+    m = xs[:2200].reshape(40, 55).copy()
+    cv.ParallelPixelFunction(m, 55, 0.7, ctx=ctx)(0, m.size)
+    assert np.array_equal(m.ravel(), kat["delta"][:2200])
+    e = np.zeros(0)
+    ctx.delta_map(e, 1.0)  # empty range is a no-op
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_csv_step_strict_bit_exact(strict, kat, name):
+    """One step with the oracle's region means given: every other operation is the reference's, in its order."""
+    img = list(kat[name + "_img"])
+    n = len(img)
+    u = kat[name + "_u"]
+    h, w = u.shape
+    c1, c2 = kat[name + "_c1"], kat[name + "_c2"]
+    ref_u1, ref_norm, _, _ = co.csv_step(img, u, _p(kat, name, n, co.params), c1, c2)
+    with cv.Session(strict, n, h, w) as s:
+        s.upload_image(img)
+        s.upload_levelset(u)
+        nrm = s.csv_step(_p(kat, name, n, cv.make_params), c1, c2)
+        u1 = s.download_levelset()
+    assert np.array_equal(u1, ref_u1)
+    assert abs(nrm - ref_norm) <= 1e-12 * ref_norm
+    assert rel_l2(u1, kat[name + "_u1"]) < 1e-13  # and the cv2 result (its own c1/c2 summation order)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_csv_run_small(ctx, kat, name):
+    img = list(kat[name + "_img"])
+    n = len(img)
+    u, steps, nrm = ctx.csv_run(img, kat[name + "_u"], _p(kat, name, n, cv.make_params), tol=0.0, max_steps=5)
+    assert steps == 5
+    assert rel_l2(u, kat[name + "_u5"]) < 1e-10
+    assert abs(nrm - kat[name + "_norm5"]) <= 1e-9 * abs(kat[name + "_norm5"])
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_pm_small(ctx, kat, name):
+    img = list(kat[name + "_img"])
+    out, n = ctx.perona_malik(img, 12.0, 0.2, 0.7)
+    assert n == int(kat[name + "_pmsteps"])
+    _planes_close(out, kat[name + "_pm"], frac=0.999)
+    ctx.set_math_mode(True)
+    try:
+        out, _ = ctx.perona_malik(img, 12.0, 0.2, 0.7)
+        assert np.array_equal(np.stack(out), kat[name + "_pm"])
+    finally:
+        ctx.set_math_mode(False)
+
+
+def test_pm_step_counts_and_zero_steps(ctx):
+    rng = np.random.default_rng(3)
+    img = [rng.integers(0, 256, size=(33, 47), dtype=np.uint8)]
+    for L, T in [(0.25, 0.25), (0.25, 0.5), (0.2, 0.7), (0.1, 0.35)]:
+        out, n = ctx.perona_malik(img, 15.0, L, T)
+        ref, nr = co.perona_malik(img, 15.0, L, T)
+        assert n == nr == synth.pm_steps_expected(L, T)
+        _planes_close(out, ref, frac=0.999)
+    out, n = ctx.perona_malik(img, 15.0, 0.25, 0.0)
+    assert n == 0 and np.array_equal(out[0], img[0])
+    flat = [np.full((20, 300), 77, dtype=np.uint8)]
+    out, _ = ctx.perona_malik(flat, 10.0, 0.25, 5.0)
+    assert np.array_equal(out[0], flat[0])  # a constant image is a fixed point
+
+
+# ---- the BASELINE configurations ---------------------------------------------------------------------------------
+def test_config1(ctx, golden_c1):
+    """README.md:53: PM -L 0.25 -T 100 -K 30 (400 steps) + CSV -N 70, checkerboard init."""
+    c = synth.CONFIGS["C1"]
+    img = synth.seastar()
+    u0 = cv.levelset_checkerboard(c["h"], c["w"])
+    assert np.array_equal(u0, co.levelset_checkerboard(c["h"], c["w"]))
+    r = ctx.segment(img, u0, cv.make_params(), tol=1e-3, max_steps=70, smooth=True, **c["pm"])
+    _planes_close(r["pm"], golden_c1["pm"])
+    # CSV on the oracle's PM planes so that a 1-LSB PM tie does not leak into the level-set comparison
+    u, steps, nrm = ctx.csv_run(list(golden_c1["pm"]), u0, cv.make_params(), tol=1e-3, max_steps=70)
+    assert steps == int(golden_c1["steps"])
+    assert rel_l2(u, golden_c1["u"]) < TOL_U
+    assert abs(nrm - float(golden_c1["norm"])) <= 1e-6 * float(golden_c1["norm"])
+    ref_mask = np.unpackbits(golden_c1["mask"])[:c["h"] * c["w"]].reshape(c["h"], c["w"])
+    assert (ctx.mask(u) == ref_mask).mean() == 1.0
+    assert (r["mask"] == ref_mask).mean() >= 0.999  # end to end, including the PM hand-off in uint8
+
+
+def test_config2(ctx, golden_c2):
+    """README.md:59-62: --dt 0.001 -t 1e-6 --nu -293 --lambda1 1 1 0.1, PM -L 0.1 -T 1.5 -K 1000 (15 steps), -N 132."""
+    c = synth.CONFIGS["C2"]
+    k = c["csv"]
+    img = synth.night_lights()
+    out, n = ctx.perona_malik(img, **c["pm"])
+    assert n == 15 == int(golden_c2["pmsteps"])
+    _planes_close(out, golden_c2["pm"])
+    p = cv.make_params(nu=k["nu"], dt=k["dt"], lambda1=k["lambda1"])
+    u, steps, nrm = ctx.csv_run(list(golden_c2["pm"]), cv.levelset_checkerboard(c["h"], c["w"]), p, tol=k["tol"],
+                                max_steps=k["max_steps"])
+    assert steps == int(golden_c2["steps"])
+    assert rel_l2(u[::4, ::4], golden_c2["u_sub"]) < TOL_U
+    assert abs(np.linalg.norm(u) - float(golden_c2["u_norm"])) <= TOL_U * float(golden_c2["u_norm"])
+    ref_mask = np.unpackbits(golden_c2["mask"])[:c["h"] * c["w"]].reshape(c["h"], c["w"])
+    assert (ctx.mask(u) == ref_mask).mean() >= 0.999
+
+
+def test_config3_reduced_ring_init(ctx):
+    """C3 (grayscale, one-pixel ring init of InteractiveDataCirc) at 512^2 for 40 steps against the oracle."""
+    img = synth.two_phase(512, 512, seed=3, discs=10)
+    u0 = cv.levelset_circ(512, 512, 256, 256, 128)
+    assert np.array_equal(u0, co.levelset_circ(512, 512, 256, 256, 128))
+    u, steps, _ = ctx.csv_run(img, u0, cv.make_params(nch=1), tol=0.0, max_steps=40)
+    ref, rs, _ = co.csv_run(img, u0, co.params(), 0.0, 40)
+    assert steps == rs == 40
+    assert rel_l2(u, ref) < TOL_U
+    assert (ctx.mask(u) == co.mask(ref)).mean() >= 0.999
+
+
+def test_early_stop_same_step_as_oracle(ctx):
+    """The tolerance ends the run (not -N): same breaking step, and its update is applied (src/main.cpp:994,1000)."""
+    img = synth.seastar(120, 150, seed=11)
+    u0 = cv.levelset_checkerboard(120, 150)
+    for tol in (0.05, 0.2):
+        ref, rs, rn = co.csv_run(img, u0, co.params(), tol, 200)
+        u, steps, nrm = ctx.csv_run(img, u0, cv.make_params(), tol=tol, max_steps=200)
+        assert rs < 200 and steps == rs
+        assert rel_l2(u, ref) < TOL_U
+        assert abs(nrm - rn) <= 1e-6 * rn
+
+
+def test_unlimited_steps_and_frame_observer(ctx):
+    img = synth.seastar(64, 80, seed=5)
+    u0 = cv.levelset_checkerboard(64, 80)
+    ref, rs, _ = co.csv_run(img, u0, co.params(), 0.1, 10 ** 6)
+    seen = []
+
+    def frame(u, step):
+        seen.append((step, float(u.sum())))
+        return 0
+
+    u, steps, _ = ctx.csv_run(img, u0, cv.make_params(), tol=0.1, max_steps=-1, frame=frame)  # -N -1 -> unlimited
+    assert steps == rs
+    assert [s for s, _ in seen] == list(range(1, steps + 1))
+    assert seen[-1][1] == pytest.approx(float(u.sum()), rel=1e-12)
+    with pytest.raises(cv.ChanVeseError) as e:
+        ctx.csv_run(img, u0, cv.make_params(), tol=0.0, max_steps=5, frame=lambda u, s: s == 2)
+    assert e.value.status == 7  # CVB_ERR_CALLBACK
+
+
+# ---- resident sessions, batches, decomposition invariance -------------------------------------------------------------
+def test_session_matches_one_shot_and_device_checkerboard(ctx):
+    img = synth.seastar(90, 131, seed=2)
+    p = cv.make_params(lambda1=[1.0, 0.5, 2.0])
+    u_ref, s_ref, _ = ctx.csv_run(img, cv.levelset_checkerboard(90, 131), p, tol=0.0, max_steps=12)
+    with cv.Session(ctx, 3, 90, 131) as s:
+        s.upload_image(img)
+        s.init_checkerboard()
+        assert np.array_equal(s.download_levelset(), cv.levelset_checkerboard(90, 131))
+        steps, _ = s.csv_run(p, tol=0.0, max_steps=12)
+        assert steps == s_ref and np.array_equal(s.download_levelset(), u_ref)
+        # continuing a run from the resident level set == running longer from the start
+        s.csv_run(p, tol=0.0, max_steps=3)
+        u15 = s.download_levelset()
+    u_long, _, _ = ctx.csv_run(img, cv.levelset_checkerboard(90, 131), p, tol=0.0, max_steps=15)
+    assert np.array_equal(u15, u_long)
+
+
+def test_tile_rows_invariance(ctx):
+    """Results must not depend on the tiling beyond summation order (1e-12), and are bit-reproducible run to run."""
+    img = synth.seastar(200, 300, seed=9)
+    u0 = cv.levelset_checkerboard(200, 300)
+    res = {}
+    try:
+        for rows in (4, 8, 32, 64):
+            ctx.set_tile_rows(rows)
+            res[rows] = ctx.csv_run(img, u0, cv.make_params(), tol=0.0, max_steps=25)[0]
+        again = ctx.csv_run(img, u0, cv.make_params(), tol=0.0, max_steps=25)[0]
+    finally:
+        ctx.set_tile_rows(0)
+    assert np.array_equal(again, res[64])
+    for rows in (4, 8, 32):
+        assert rel_l2(res[rows], res[64]) < 1e-11
+    pm = {}
+    try:
+        for rows in (4, 32):
+            ctx.set_tile_rows(rows)
+            pm[rows] = ctx.perona_malik(img, 30.0, 0.25, 3.0)[0]
+    finally:
+        ctx.set_tile_rows(0)
+    assert all(np.array_equal(a, b) for a, b in zip(pm[4], pm[32]))  # PM has no reductions: bit-identical
+
+
+def test_batch_equals_sessions(ctx):
+    """Image-parallel batches (BASELINE config 5): independent c1/c2, stop flags and step counts per image."""
+    count, h, w = 6, 96, 112
+    imgs = synth.batch_images(0, count, h, w)
+    u0 = cv.levelset_checkerboard(h, w)
+    p = cv.make_params()
+    ctx.set_tile_rows(8)  # the automatic tiling depends on the image count; fix it so the sums add in the same order
+    try:
+        with cv.Batch(ctx, count, 3, h, w) as b:
+            b.upload_images(imgs)
+            b.upload_levelset(u0)
+            assert b.perona_malik(30.0, 0.25, 2.0) == 8
+            steps, norms = b.csv_run(p, tol=0.08, max_steps=60)
+            got = [(b.download_image(m), b.download_levelset(m), b.mask(m)) for m in range(count)]
+        single = [ctx.segment(list(imgs[m]), u0, p, tol=0.08, max_steps=60, smooth=True, K=30.0, L=0.25, T=2.0)
+                  for m in range(count)]
+    finally:
+        ctx.set_tile_rows(0)
+    assert len(set(steps.tolist())) > 1  # early stops differ per image
+    for m in range(count):
+        r = single[m]
+        assert all(np.array_equal(a, b) for a, b in zip(got[m][0], r["pm"]))
+        assert steps[m] == r["steps"]
+        assert np.array_equal(got[m][1], r["u"])
+        assert np.array_equal(got[m][2], r["mask"])
+        assert norms[m] == r["norm"]
+    # and against the oracle for one of them
+    pm_ref, _ = co.perona_malik(list(imgs[2]), 30.0, 0.25, 2.0)
+    _planes_close(got[2][0], pm_ref, frac=0.999)
+    u_ref, s_ref, _ = co.csv_run(got[2][0], u0, co.params(), 0.08, 60)
+    assert steps[2] == s_ref and rel_l2(got[2][1], u_ref) < TOL_U
+
+
+# ---- full BASELINE sizes ---------------------------------------------------------------------------------------------
+def test_config3_full_size_few_steps(ctx):
+    """4096^2 grayscale, ring init: 3 steps against the oracle (a few seconds of CPU)."""
+    img = synth.two_phase()
+    u0 = cv.levelset_circ(4096, 4096, 2048, 2048, 1024)
+    u, steps, nrm = ctx.csv_run(img, u0, cv.make_params(nch=1), tol=0.0, max_steps=3)
+    ref, rs, rn = co.csv_run(img, u0, co.params(), 0.0, 3)
+    assert steps == rs == 3
+    assert rel_l2(u, ref) < 1e-9
+    assert abs(nrm - rn) <= 1e-9 * rn
+    assert (ctx.mask(u) == co.mask(ref)).mean() >= 0.999
+
+
+def test_config4_full_size_windows(ctx):
+    """16384^2 RGB: one PM step and one CSV step with given region means are local stencils, so windows of the
+    full-size result must equal the oracle run on the same window plus its halo -- bit-exact in strict math."""
+    h = w = 16384
+    rng = np.random.default_rng(4)
+    img = [rng.integers(0, 256, size=(h, w), dtype=np.uint8) for _ in range(3)]
+    c1, c2 = np.array([100.0, 120.5, 90.25]), np.array([140.0, 99.0, 131.0])
+    p_gpu, p_ref = cv.make_params(lambda1=[1.0, 0.5, 2.0]), co.params(lambda1=[1.0, 0.5, 2.0])
+    ctx.set_math_mode(True)
+    try:
+        with cv.Session(ctx, 3, h, w) as s:
+            s.upload_image(img)
+            s.init_checkerboard()
+            assert s.perona_malik(25.0, 0.25, 0.5) == 2
+            pm = s.download_image()
+            s.csv_step(p_gpu, c1, c2)
+            u1 = s.download_levelset()
+            m1 = s.mask()
+    finally:
+        ctx.set_math_mode(False)
+    u0 = None
+    wins = [(0, 0), (0, w - 96), (h - 96, 0), (h - 96, w - 96), (8000, 8100), (4090, 12345), (16000, 300)]
+    for (r0, c0) in wins:
+        ra, rb = max(r0 - 8, 0), min(r0 + 96 + 8, h)
+        ca, cb = max(c0 - 8, 0), min(c0 + 96 + 8, w)
+        # PM window: two steps reach 4 pixels; compare the inner 96x96 (or up to the true border)
+        sub = [np.ascontiguousarray(x[ra:rb, ca:cb]) for x in img]
+        ref_pm = [co.pm_evolve(x, 25.0, 0.25, 2) for x in sub]
+        ir = slice(0 if ra == 0 else 8, (rb - ra) if rb == h else (rb - ra - 8))
+        ic = slice(0 if ca == 0 else 8, (cb - ca) if cb == w else (cb - ca - 8))
+        for k in range(3):
+            q = np.clip(np.rint(ref_pm[k]), 0, 255).astype(np.uint8)
+            # windows that do not touch the true border see clamped neighbours at their cut edges: inner part only
+            assert np.array_equal(q[ir, ic], pm[k][ra:rb, ca:cb][ir, ic])
+        if u0 is None:
+            u0 = cv.levelset_checkerboard(h, w)
+        subpm = [np.ascontiguousarray(x[ra:rb, ca:cb]) for x in pm]
+        ref_u1, _, _, _ = co.csv_step(subpm, u0[ra:rb, ca:cb], p_ref, c1, c2)
+        assert np.array_equal(ref_u1[ir, ic], u1[ra:rb, ca:cb][ir, ic])
+    assert np.array_equal(m1, (u1.astype(np.float32) > 0).astype(np.uint8))
