@@ -486,6 +486,7 @@ static void fill_args(const Job *j, const cvb_csv_params *p, double tol, CsvArgs
             A.lambda2[k] = p->lambda2[k];
         }
     }
+    A.inv_eps = 1.0 / A.eps;
     A.tol = tol;
     A.multi_rank = (j->slab && j->ctx->nranks > 1) ? 1 : 0;
     A.ngroups_local = j->ngroups_local;

@@ -69,7 +69,7 @@ struct CsvArgs {
     double *kappa_out;      // MODE_KAPPA only
     const double *atan_tab; // 34 entries, see math.cuh
     double alpha, beta, gamma;  // mu*dt, (1/N)*dt, -nu*dt (src/main.cpp:985 as one addWeighted)
-    double eps;
+    double eps, inv_eps;
     double lambda1[MAX_CH], lambda2[MAX_CH];
     double tol;
     int multi_rank;         // 1: stop after the group sums; csv_finalize runs after the all-gather

@@ -28,13 +28,157 @@ namespace cvb {
 
 enum { MODE_STEP = 0, MODE_KAPPA = 1 };
 
+
+// Coefficients of one step, derived from the region means once per thread.
+template <int NCH>
+struct StepCoef {
+    double cA[NCH], cB[NCH];  // per-channel data term as a quadratic in I: A_k I^2 + B_k I
+    double q0;                // constant part: gamma' + sum_k C_k
+    double alphap;            // mu*dt * eps/pi
+    double eps2, inv_eps;
+};
+
+// ---- interior fast path ---------------------------------------------------------------------------------
+// For CTAs whose stencils never touch an image border (all but the outermost ring of CTAs): no clamping,
+// no border selects, no validity masks; the row recurrence carries u(i) - u(i-1) instead of row i-1, so
+// only two row ages are live and a 2x unrolled loop needs no register moves.  One output row per iteration:
+//   in:  C = u(i,.), dN = u(i,.) - u(i-1,.), nyp = ny(i-1,.), S = u(i+1,.)
+template <int NCH>
+__device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, double *__restrict__ uout,
+                                              const uint8_t *__restrict__ im, const Geom &G, const StepCoef<NCH> &K,
+                                              const double *s_tab, int ra, int rb, int a, int lane, double (&acc)[NACC]) {
+    const size_t pitch = (size_t)G.pitch;
+    const double *pu = uin + (size_t)(ra - 2 - G.row_lo + HALO) * pitch + a;  // row ra-2
+    double *po = uout + (size_t)(ra - G.row_lo + HALO) * pitch + a;           // row ra
+    const uint8_t *pi = im + (size_t)(ra - G.row_lo + HALO) * pitch + a;      // row ra, channel 0
+    const size_t pe = (size_t)G.plane_elems;
+    const bool l31 = lane == 31;
+
+    // prime: rows ra-2, ra-1, ra
+    const double2 R0 = __ldg(reinterpret_cast<const double2 *>(pu));
+    const double2 R1 = __ldg(reinterpret_cast<const double2 *>(pu + pitch));
+    double2 C = __ldg(reinterpret_cast<const double2 *>(pu + 2 * pitch));
+    double e2c = l31 ? __ldg(pu + 2 * pitch + 2) : 0.0;
+    double dN0 = C.x - R1.x, dN1 = C.y - R1.y;
+    double nyp0 = normal_component<false>(dN0, dN0 + (R1.x - R0.x));
+    double nyp1 = normal_component<false>(dN1, dN1 + (R1.y - R0.y));
+    pu += 3 * pitch;  // row ra+1
+
+    // register prefetch: rows i+1 and i+2 of u, rows i and i+1 of the image
+    double2 q0 = __ldg(reinterpret_cast<const double2 *>(pu)), q1 = make_double2(0.0, 0.0);
+    double f0 = l31 ? __ldg(pu + 2) : 0.0, f1 = 0.0;
+    unsigned int j0[NCH], j1[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        j0[c] = __ldg(reinterpret_cast<const unsigned short *>(pi + c * pe));
+        j1[c] = 0u;
+    }
+    const int n = rb - ra;
+    if (n > 1) {
+        q1 = __ldg(reinterpret_cast<const double2 *>(pu + pitch));
+        if (l31) f1 = __ldg(pu + pitch + 2);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) j1[c] = __ldg(reinterpret_cast<const unsigned short *>(pi + pitch + c * pe));
+    }
+    pu += 2 * pitch;  // row ra+3: next row to fetch
+    pi += 2 * pitch;  // row ra+2
+
+    double accA = 0.0, accS = 0.0, accI[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) accI[c] = 0.0;
+
+#pragma unroll 2
+    for (int r = 0; r < n; ++r) {
+        const double2 S = q0;
+        const double e2s = f0;
+        unsigned int Ib[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) Ib[c] = j0[c];
+        q0 = q1;
+        f0 = f1;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) j0[c] = j1[c];
+        if (r + 2 < n) {  // rows (ra+r)+3 of u and (ra+r)+2 of the image
+            q1 = __ldg(reinterpret_cast<const double2 *>(pu));
+            if (l31) f1 = __ldg(pu + 2);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) j1[c] = __ldg(reinterpret_cast<const unsigned short *>(pi + c * pe));
+        }
+        if (r + CSV_PF < n) {
+            prefetch_l2(pu + (size_t)(CSV_PF - 2) * pitch);
+            if (lane < 3 * NCH) prefetch_l2(pi + (size_t)(CSV_PF - 2) * pitch + (lane / 3) * pe + (2 - 2 * lane + (lane % 3) * 31));
+        }
+        pu += pitch;
+        pi += pitch;
+
+        // curvature (:342-375)
+        const double upy0 = S.x - C.x, upy1 = S.y - C.y;
+        const double ny0 = normal_component<false>(upy0, upy0 + dN0);
+        const double ny1 = normal_component<false>(upy1, upy1 + dN1);
+        const double Wn = __shfl_up_sync(0xffffffffu, C.y, 1);
+        double E2 = __shfl_down_sync(0xffffffffu, C.x, 1);
+        E2 = l31 ? e2c : E2;
+        const double nx0 = normal_component<false>(C.y - C.x, C.y - Wn);
+        const double nx1 = normal_component<false>(E2 - C.y, E2 - C.x);
+        const double nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
+        const double kap0 = (nx0 - nxw) + (ny0 - nyp0);
+        const double kap1 = (nx1 - nx0) + (ny1 - nyp1);
+        // data term + combine (:968-985), delta (:988-992), update (:994)
+        double I0[NCH], I1[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            I0[c] = u8_to_double(Ib[c] & 0xffu);
+            I1[c] = u8_to_double(Ib[c] >> 8);
+        }
+        double t0 = K.q0, t1 = K.q0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            t0 = fma(fma(K.cA[c], I0[c], K.cB[c]), I0[c], t0);
+            t1 = fma(fma(K.cA[c], I1[c], K.cB[c]), I1[c], t1);
+        }
+        t0 = fma(kap0, K.alphap, t0);
+        t1 = fma(kap1, K.alphap, t1);
+        const double du0 = t0 * fast_rcp(fma(C.x, C.x, K.eps2));
+        const double du1 = t1 * fast_rcp(fma(C.y, C.y, K.eps2));
+        const double un0 = C.x + du0, un1 = C.y + du1;
+        if (lane) *reinterpret_cast<double2 *>(po) = make_double2(un0, un1);
+        po += pitch;
+        // sums of the updated level set and of du^2 (lane 0 is a halo lane: its sums are dropped at the end)
+        const double a0 = atan_over_pi(un0 * K.inv_eps, s_tab);
+        const double a1 = atan_over_pi(un1 * K.inv_eps, s_tab);
+        accA += a0;
+        accA += a1;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            accI[c] = fma(I0[c], a0, accI[c]);
+            accI[c] = fma(I1[c], a1, accI[c]);
+        }
+        accS = fma(du0, du0, accS);
+        accS = fma(du1, du1, accS);
+        // next row
+        dN0 = upy0;
+        dN1 = upy1;
+        nyp0 = ny0;
+        nyp1 = ny1;
+        C = S;
+        e2c = e2s;
+    }
+    if (lane) {
+        acc[ACC_A] = accA;
+        acc[ACC_SQ] = accS;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = accI[c];
+    }
+}
+
 template <int NCH, bool STRICT, int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, 4) csv_step_kernel(const __grid_constant__ CsvArgs A) {
     const Geom &G = A.g;
     __shared__ double s_tab[ATAN_TAB_N];
     __shared__ double s_red[NACC][CTA_THREADS];
     __shared__ int s_flag;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the value is warp-uniform
     int bid = blockIdx.x;
     const int cb = bid % G.ncb_csv;
     bid /= G.ncb_csv;
@@ -61,31 +205,41 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) csv_step_kernel(const __grid_c
 
     // ---- per-step coefficients
     const double eps = A.eps;
-    const double inv_eps = 1.0 / eps;
+    const double inv_eps = A.inv_eps;
     // fast: du = (kappa*alpha' + sum_k (A_k I^2 + B_k I) + q0) / (eps^2 + u^2), everything pre-scaled by eps/pi
-    double cA[NCH], cB[NCH], q0 = 0.0, alphap = 0.0, eps2 = eps * eps;
+    StepCoef<NCH> K;
+    K.q0 = 0.0;
+    K.alphap = 0.0;
+    K.eps2 = eps * eps;
+    K.inv_eps = inv_eps;
     double c1[NCH], c2[NCH];
     if (MODE == MODE_STEP) {
         const double kd = eps * CVB_INV_PI;
         const double bk = A.beta * kd;
-        alphap = A.alpha * kd;
-        q0 = A.gamma * kd;
+        K.alphap = A.alpha * kd;
+        K.q0 = A.gamma * kd;
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
             c1[k] = st->c1[k];
             c2[k] = st->c2[k];
             const double l1 = A.lambda1[k], l2 = A.lambda2[k];
-            cA[k] = bk * (l2 - l1);
-            cB[k] = 2.0 * bk * (l1 * c1[k] - l2 * c2[k]);
-            q0 += bk * (l2 * c2[k] * c2[k] - l1 * c1[k] * c1[k]);
+            K.cA[k] = bk * (l2 - l1);
+            K.cB[k] = 2.0 * bk * (l1 * c1[k] - l2 * c2[k]);
+            K.q0 += bk * (l2 * c2[k] * c2[k] - l1 * c1[k] * c1[k]);
         }
     }
+    const double q0 = K.q0, alphap = K.alphap, eps2 = K.eps2;
+    const double *cA = K.cA, *cB = K.cB;
 
     double acc[NACC];
 #pragma unroll
     for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
 
-    if (cs < w) {
+    // CTAs whose stencils stay inside the image take the fast path (all but the outermost ring)
+    const bool interior = !STRICT && MODE == MODE_STEP && cb > 0 && (cb + 1) * CSV_CB < w && ra >= 2 && rb < h;
+    if (interior) {
+        csv_rows_fast<NCH>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
+    } else if (cs < w) {
         const int nk = rb - ra + 3;  // streamed rows ra-2 .. rb
         double2 pq[CSV_D];
         double pe[CSV_D];
@@ -277,7 +431,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) csv_init_kernel(const __grid_c
     const int cs = cb * CSV_CB + warp * CSV_STRIP_OWN;
     const int a = cs - 2 + 2 * lane;
     const int w = G.w;
-    const double inv_eps = 1.0 / A.eps;
+    const double inv_eps = A.inv_eps;
     const double inv_n = 1.0 / (double)NCH;  // Mat /= N multiplies by 1/N (src/main.cpp:958)
     double acc[NACC];
 #pragma unroll

@@ -53,9 +53,9 @@ __device__ __forceinline__ double u8_to_double(unsigned int v) {
 }
 
 // ---- atan(x)/pi ------------------------------------------------------------------------------------
-// t = |x|.  t < 2^-4: c = 0.  2^-4 <= t < 2^4: c = centre of t's quarter-octave (exponent and top two
-// mantissa bits of t kept, third bit set).  atan t = atan c + atan z, z = (t-c)/(1+t*c), |z| <= 1/16.
-// t >= 2^4: atan t = pi/2 + atan(-1/t).  tab[0] = 0, tab[1+q] = atan(c_q)/pi (q = 0..31), tab[33] = 1/2.
+// t = |x|.  t < 2^4: c = centre of the quarter-octave of max(t, 2^-4) (exponent and top two mantissa bits kept,
+// third bit set); atan t = atan c + atan z, z = (t-c)/(1+t*c), |z| <= 0.0704.  t >= 2^4: atan t = pi/2 +
+// atan(-1/t).  tab[1+q] = atan(c_q)/pi (q = 0..31), tab[33] = 1/2 (tab[0] unused).
 constexpr int ATAN_TAB_N = 34;
 constexpr int ATAN_Q0 = 1019 * 4;  // (biased exponent of 2^-4) * 4
 
@@ -63,12 +63,13 @@ __device__ __forceinline__ double atan_over_pi(double x, const double *tab /* sh
     const int hx = __double2hiint(x);
     const int ht = hx & 0x7fffffff;
     const double t = __hiloint2double(ht, __double2loint(x));
-    const int q = (ht >> 18) - ATAN_Q0;
-    const bool big = q >= 32;
-    const bool mid = q >= 0 && !big;
-    const double c = __hiloint2double(mid ? ((ht & 0xfffc0000) | 0x00020000) : 0, 0);
-    const int idx = min(max(q + 1, 0), 33);
-    const double hi = tab[idx];
+    // t < 2^-4 shares the first interval's centre: |z| <= 0.0704 and the ABSOLUTE error stays ~1e-17, which is
+    // what the sums of a = H - 1/2 need (no separate small-argument branch)
+    const int hc = max(ht, 0x3fb00000);
+    const int q1 = (hc >> 18) - (ATAN_Q0 - 1);  // >= 1
+    const bool big = q1 > 32;
+    const double c = __hiloint2double((hc & 0xfffc0000) | 0x00020000, 0);
+    const double hi = tab[min(q1, 33)];
     const double num = big ? -1.0 : t - c;
     const double den = big ? t : fma(t, c, 1.0);
     const double z = num * fast_rcp(den);
@@ -79,9 +80,9 @@ __device__ __forceinline__ double atan_over_pi(double x, const double *tab /* sh
     p = fma(p, w, 1.0 / 5.0);
     p = fma(p, w, -1.0 / 3.0);
     const double zw = z * w;
-    const double at = fma(zw, p, z);          // atan z
-    const double r = fma(at, CVB_INV_PI, hi);  // >= 0
-    return __hiloint2double(__double2hiint(r) | (hx & 0x80000000), __double2loint(r));
+    const double at = fma(zw, p, z);           // atan z
+    const double r = fma(at, CVB_INV_PI, hi);  // atan(t)/pi
+    return __hiloint2double(__double2hiint(r) ^ (hx & 0x80000000), __double2loint(r));
 }
 
 // ---- curvature normal component n = up / sqrt(up^2 + uc^2 + eta^2), src/main.cpp:365-368 --------------
