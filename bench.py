@@ -158,7 +158,7 @@ def run_b200(args):
     h = w = args.size
     stream = torch.cuda.Stream()
     ctx = cv.Context(local, stream=stream.cuda_stream)
-    tile_rows = cv.auto_tile_rows(h, w, 1)
+    tile_rows = args.tile_rows or cv.auto_tile_rows(h, w, 1)
     ctx.set_tile_rows(tile_rows)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -276,6 +276,7 @@ def main():
     ap.add_argument("--size", type=int, default=16384, help="image side (default: the BASELINE 16384)")
     ap.add_argument("--cpu-size", type=int, default=1024, help="side of the CPU-baseline crop")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tile-rows", type=int, default=0, help="rows per tile (0 = the library's automatic choice)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,6 +39,7 @@ def build(force=False, verbose=False, extra_flags=()):
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    extra_flags = list(extra_flags) + os.environ.get("CVB_EXTRA_NVCC_FLAGS", "").split()  # tuning sweeps only
     cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)

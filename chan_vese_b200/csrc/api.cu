@@ -207,9 +207,9 @@ extern "C" cvb_status cvb_levelset_circ(int h, int w, int cx, int cy, int radius
 }
 
 static int auto_seg_rows(int h, int w, int count) {
-    const long long target = 2LL * 148 * 4;  // two waves of 4 CTAs per SM
+    const long long target = 2LL * 148 * 4;  // two waves of 4 CTAs per SM; long segments amortise the row priming
     const int ncb = ceil_div(w, CSV_CB);
-    const int cands[] = {32, 16, 8, 4};
+    const int cands[] = {128, 64, 32, 16, 8, 4};
     for (int s : cands)
         if ((long long)count * ceil_div(h, s) * ncb >= target) return s;
     return 4;
@@ -657,6 +657,7 @@ static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *st
     PmArgs A;
     A.K = K;
     A.L = L;
+    A.inv_k2 = 1.0 / (K * K);
     A.g = g;
     CU(c, cudaEventRecord(c->ev[0], c->stream));
     for (int s = 1; s <= nsteps; ++s) {

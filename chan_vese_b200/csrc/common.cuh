@@ -80,7 +80,7 @@ struct CsvArgs {
 struct PmArgs {
     const void *in;   // double* or uint8_t* (first step), count*nch planes
     void *out;        // double* or uint8_t* (last step)
-    double K, L;
+    double K, L, inv_k2;
     Geom g;
 };
 

@@ -25,6 +25,9 @@ namespace cvb {
 #ifndef CSV_PF
 #define CSV_PF 8
 #endif
+#ifndef CSV_MIN_CTAS
+#define CSV_MIN_CTAS 4
+#endif
 
 enum { MODE_STEP = 0, MODE_KAPPA = 1 };
 
@@ -94,6 +97,14 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
         unsigned int Ib[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) Ib[c] = j0[c];
+#ifdef CSV_FAST_D1
+        if (r + 1 < n) {  // one row ahead only: rows (ra+r)+2 of u and (ra+r)+1 of the image
+            q0 = __ldg(reinterpret_cast<const double2 *>(pu - pitch));
+            if (l31) f0 = __ldg(pu - pitch + 2);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) j0[c] = __ldg(reinterpret_cast<const unsigned short *>(pi - pitch + c * pe));
+        }
+#else
         q0 = q1;
         f0 = f1;
 #pragma unroll
@@ -104,6 +115,7 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
 #pragma unroll
             for (int c = 0; c < NCH; ++c) j1[c] = __ldg(reinterpret_cast<const unsigned short *>(pi + c * pe));
         }
+#endif
         if (r + CSV_PF < n) {
             prefetch_l2(pu + (size_t)(CSV_PF - 2) * pitch);
             if (lane < 3 * NCH) prefetch_l2(pi + (size_t)(CSV_PF - 2) * pitch + (lane / 3) * pe + (2 - 2 * lane + (lane % 3) * 31));
@@ -172,7 +184,7 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
 }
 
 template <int NCH, bool STRICT, int MODE>
-__global__ void __launch_bounds__(CTA_THREADS, 4) csv_step_kernel(const __grid_constant__ CsvArgs A) {
+__global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(const __grid_constant__ CsvArgs A) {
     const Geom &G = A.g;
     __shared__ double s_tab[ATAN_TAB_N];
     __shared__ double s_red[NACC][CTA_THREADS];
@@ -228,6 +240,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) csv_step_kernel(const __grid_c
             K.q0 += bk * (l2 * c2[k] * c2[k] - l1 * c1[k] * c1[k]);
         }
     }
+#ifdef CSV_UNIFORM_COEF
+    // every lane computed the same numbers; reading them back from lane 0 tells the compiler they are warp-uniform,
+    // so they can live in uniform registers instead of 20 per-thread registers
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        K.cA[k] = __shfl_sync(0xffffffffu, K.cA[k], 0);
+        K.cB[k] = __shfl_sync(0xffffffffu, K.cB[k], 0);
+    }
+    K.q0 = __shfl_sync(0xffffffffu, K.q0, 0);
+    K.alphap = __shfl_sync(0xffffffffu, K.alphap, 0);
+    K.eps2 = __shfl_sync(0xffffffffu, K.eps2, 0);
+    K.inv_eps = __shfl_sync(0xffffffffu, K.inv_eps, 0);
+#endif
     const double q0 = K.q0, alphap = K.alphap, eps2 = K.eps2;
     const double *cA = K.cA, *cB = K.cB;
 

@@ -82,10 +82,97 @@ __device__ __forceinline__ double pm_update(double I0, double IS, double IE, dou
     }
 }
 
+
+// ---- interior fast path ---------------------------------------------------------------------------------------
+// For CTAs whose stencils never touch an image border.  The update is written in flux form: with
+//   Fy(i+1/2,j) = (g(i,j) + g(i+1,j)) * (I(i+1,j) - I(i,j)),   Fx(i,j+1/2) = (g(i,j) + g(i,j+1)) * (I(i,j+1) - I(i,j))
+// the reference's four terms are  Fy(i+1/2) - Fy(i-1/2) + Fx(j+1/2) - Fx(j-1/2)  (each product bit-identical to the
+// reference's; only the order of the final additions differs), so every flux is computed once: the south flux is
+// carried to the next row and the west flux comes from the neighbouring lane.  All row queues are two deep, so a
+// 2x unrolled loop needs no register moves.  Per iteration: row i+2 arrives, g(i+1) is finished, row i is written.
+template <typename TIN, typename TOUT>
+__device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *__restrict__ out, const Geom &G, int ra,
+                                             int rb, int a, int lane, double inv_k2, double lq) {
+    const size_t pitch = (size_t)G.pitch;
+    const TIN *pin = in + (size_t)(ra - 2 - G.row_lo + HALO) * pitch + a;  // row ra-2
+    TOUT *po = out + (size_t)(ra - G.row_lo + HALO) * pitch + a;           // row ra
+    const int n = rb - ra;
+
+    auto sobel_rows = [&](const double2 &X, double2 &rd, double2 &rs) {  // separable Sobel, row pass
+        const double Wn = __shfl_up_sync(0xffffffffu, X.y, 1);
+        const double E2 = __shfl_down_sync(0xffffffffu, X.x, 1);
+        rd.x = X.y - Wn;
+        rs.x = fma(2.0, X.x, Wn) + X.y;
+        rd.y = E2 - X.x;
+        rs.y = fma(2.0, X.y, X.x) + E2;
+    };
+    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, gy * gy), inv_k2, 1.0)); };  // :518-521
+
+    // prologue: rows ra-2 .. ra+1 give g(ra-1), g(ra) and the flux Fy(ra-1/2)
+    const double2 X0 = pm_load2<TIN>(pin), X1 = pm_load2<TIN>(pin + pitch), X2 = pm_load2<TIN>(pin + 2 * pitch),
+                  X3 = pm_load2<TIN>(pin + 3 * pitch);
+    double2 rd0, rs0, rd1, rs1, rd2, rs2, rd3, rs3;
+    sobel_rows(X0, rd0, rs0);
+    sobel_rows(X1, rd1, rs1);
+    sobel_rows(X2, rd2, rs2);
+    sobel_rows(X3, rd3, rs3);
+    double2 gP, gC;  // g(ra-1), g(ra)
+    gP.x = edge((rd0.x + 2.0 * rd1.x) + rd2.x, rs2.x - rs0.x);
+    gP.y = edge((rd0.y + 2.0 * rd1.y) + rd2.y, rs2.y - rs0.y);
+    gC.x = edge((rd1.x + 2.0 * rd2.x) + rd3.x, rs3.x - rs1.x);
+    gC.y = edge((rd1.y + 2.0 * rd2.y) + rd3.y, rs3.y - rs1.y);
+    double fy0 = (gP.x + gC.x) * (X2.x - X1.x), fy1 = (gP.y + gC.y) * (X2.y - X1.y);  // Fy(ra-1/2)
+    double2 IC = X2, IS = X3;                                                  // rows i, i+1
+    double2 P = make_double2(fma(2.0, rd3.x, rd2.x), fma(2.0, rd3.y, rd2.y));  // rd(i) + 2 rd(i+1)
+    double2 rdB = rd3;                                                         // rd(i+1)
+    double2 rsA = rs2, rsB = rs3;                                              // rs(i), rs(i+1)
+    pin += 4 * pitch;                                                          // row ra+2
+    double2 q0 = pm_load2<TIN>(pin), q1 = make_double2(0.0, 0.0);
+    if (n > 1) q1 = pm_load2<TIN>(pin + pitch);
+    pin += 2 * pitch;  // row ra+4: next row to fetch
+#pragma unroll 2
+    for (int r = 0; r < n; ++r) {
+        const double2 X = q0;  // row i+2
+        q0 = q1;
+        if (r + 2 < n) q1 = pm_load2<TIN>(pin);
+        if (r + PM_PF < n) prefetch_l2(pin + (size_t)(PM_PF - 2) * pitch);
+        pin += pitch;
+        // g(i+1) from the Sobel sums of rows i, i+1, i+2 (:503-504, :513-522)
+        double2 rdC, rsC;
+        sobel_rows(X, rdC, rsC);
+        double2 gS;
+        gS.x = edge(P.x + rdC.x, rsC.x - rsA.x);
+        gS.y = edge(P.y + rdC.y, rsC.y - rsA.y);
+        // fluxes of row i and the update (:524-548)
+        const double fs0 = (gC.x + gS.x) * (IS.x - IC.x), fs1 = (gC.y + gS.y) * (IS.y - IC.y);  // Fy(i+1/2)
+        const double Ie = __shfl_down_sync(0xffffffffu, IC.x, 1);
+        const double ge = __shfl_down_sync(0xffffffffu, gC.x, 1);
+        const double fx0 = (gC.x + gC.y) * (IC.y - IC.x);        // Fx(a+1/2)
+        const double fx1 = (gC.y + ge) * (Ie - IC.y);            // Fx(a+3/2)
+        const double fxw = __shfl_up_sync(0xffffffffu, fx1, 1);  // Fx(a-1/2)
+        const double o0 = fma((fs0 - fy0) + (fx0 - fxw), lq, IC.x);
+        const double o1 = fma((fs1 - fy1) + (fx1 - fx0), lq, IC.y);
+        if (lane >= 1 && lane <= 30) pm_store(po, o0, o1, true);
+        po += pitch;
+        // next row
+        fy0 = fs0;
+        fy1 = fs1;
+        P.x = fma(2.0, rdC.x, rdB.x);
+        P.y = fma(2.0, rdC.y, rdB.y);
+        rdB = rdC;
+        rsA = rsB;
+        rsB = rsC;
+        IC = IS;
+        IS = X;
+        gC = gS;
+    }
+}
+
 template <typename TIN, typename TOUT, bool STRICT>
 __global__ void __launch_bounds__(CTA_THREADS, 4) pm_step_kernel(const __grid_constant__ PmArgs A) {
     const Geom &G = A.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the value is warp-uniform
     int bid = blockIdx.x;
     const int cb = bid % G.ncb_pm;
     bid /= G.ncb_pm;
@@ -102,7 +189,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) pm_step_kernel(const __grid_co
     const int w = G.w, h = G.h;
     const bool colok = a >= 0 && a < G.pitch;
     const double K = A.K, L = A.L;
-    const double inv_k2 = 1.0 / (K * K), lq = L * 0.25;
+    const double inv_k2 = A.inv_k2, lq = L * 0.25;
+    // CTAs whose stencils stay inside the image take the fast path (all but the outermost ring)
+    if (!STRICT && cb >= 1 && (cb + 1) * PM_CB + 2 <= w && ra >= 2 && rb <= h - 2) {
+        pm_rows_fast<TIN, TOUT>(in, out, G, ra, rb, a, lane, inv_k2, lq);
+        return;
+    }
 
     const int nk = rb - ra + 4;  // streamed rows ra-2 .. rb+1
     auto row_off = [&](int k) -> size_t {
