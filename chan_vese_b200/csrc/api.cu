@@ -207,7 +207,7 @@ extern "C" cvb_status cvb_levelset_circ(int h, int w, int cx, int cy, int radius
 }
 
 static int auto_seg_rows(int h, int w, int count) {
-    const long long target = 2LL * 148 * 4;  // two waves of 4 CTAs per SM; long segments amortise the row priming
+    const long long target = 2LL * 148 * 20;  // two waves of 20 one-warp CTAs per SM; long segments amortise the row priming
     const int ncb = ceil_div(w, CSV_CB);
     const int cands[] = {128, 64, 32, 16, 8, 4};
     for (int s : cands)

@@ -15,13 +15,14 @@
 namespace cvb {
 
 constexpr int HALO = 2;            // halo rows above and below a slab (PM needs 2/2, CSV 2/1)
-constexpr int WARPS_PER_CTA = 4;   // a CTA = 4 warps = 4 adjacent column strips of one row segment
+constexpr int WARPS_PER_CTA = 1;   // a CTA = one warp = one column strip of one row segment: no block barriers,
+                                   // a finished warp frees its slot immediately (up to 32 resident CTAs per SM)
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr int STRIP_LANES = 64;    // columns touched by a warp: each lane owns 2 adjacent columns
 constexpr int CSV_STRIP_OWN = 62;  // lane 0 is a halo lane (it supplies nx of the column to the left)
 constexpr int PM_STRIP_OWN = 60;   // lanes 0 and 31 are halo lanes (radius-2 stencil)
-constexpr int CSV_CB = WARPS_PER_CTA * CSV_STRIP_OWN;  // 248 columns per CTA
-constexpr int PM_CB = WARPS_PER_CTA * PM_STRIP_OWN;    // 240 columns per CTA
+constexpr int CSV_CB = WARPS_PER_CTA * CSV_STRIP_OWN;  // columns per CTA
+constexpr int PM_CB = WARPS_PER_CTA * PM_STRIP_OWN;    // columns per CTA
 constexpr int MAX_CH = 3;
 // Accumulator slots of the fused reductions.  a(u) = atan(u/eps)/pi = H(u) - 1/2 (src/main.cpp:188-194):
 //   [0] sum a   [1..3] sum I_k*a   [4] sum du^2 (step) or sum mean_k(I)^2 (init)   [5..7] sum I_k (init)
@@ -64,7 +65,7 @@ struct CsvArgs {
     double *u[2];           // ping-pong level-set buffers, count planes each
     const uint8_t *img;     // count * nch planes
     CsvState *state;        // count
-    double *partials;       // [count][nseg][ncb][WARPS_PER_CTA][NACC]
+    double *partials;       // [count][nseg][ncb][NACC]
     double *group_sums;     // [NGROUPS][count][NACC]
     double *kappa_out;      // MODE_KAPPA only
     const double *atan_tab; // 34 entries, see math.cuh

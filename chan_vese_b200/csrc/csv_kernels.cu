@@ -26,7 +26,10 @@ namespace cvb {
 #define CSV_PF 8
 #endif
 #ifndef CSV_MIN_CTAS
-#define CSV_MIN_CTAS 4
+#define CSV_MIN_CTAS 20  // one-warp CTAs: 20 resident warps per SM = 96 registers per thread
+#endif
+#ifndef CSV_NO_UNIFORM_COEF
+#define CSV_UNIFORM_COEF 1
 #endif
 
 enum { MODE_STEP = 0, MODE_KAPPA = 1 };
@@ -186,22 +189,22 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
 template <int NCH, bool STRICT, int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(const __grid_constant__ CsvArgs A) {
     const Geom &G = A.g;
-    __shared__ double s_tab[ATAN_TAB_N];
-    __shared__ double s_red[NACC][CTA_THREADS];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the value is warp-uniform
+    __shared__ double s_tab[ATAN_TAB_N + 2];
+    const int lane = threadIdx.x;
+    constexpr int warp = 0;
     int bid = blockIdx.x;
     const int cb = bid % G.ncb_csv;
     bid /= G.ncb_csv;
     const int seg = bid % G.nseg;
     const int img = bid / G.nseg;
     CsvState *st = A.state + img;
-    if (MODE == MODE_STEP && st->done) return;  // frozen image: the launch is a no-op (src/main.cpp:1000)
-    if (tid < ATAN_TAB_N) s_tab[tid] = A.atan_tab[tid];
-    __syncthreads();
+    const int2 ds = *reinterpret_cast<const int2 *>(&st->done);  // {done, steps_done}
+    s_tab[lane] = A.atan_tab[lane];
+    if (lane < ATAN_TAB_N - 32) s_tab[32 + lane] = A.atan_tab[32 + lane];
+    if (MODE == MODE_STEP && ds.x) return;  // frozen image: the launch is a no-op (src/main.cpp:1000)
+    __syncwarp();
 
-    const int par = st->steps_done & 1;
+    const int par = ds.y & 1;
     const double *__restrict__ uin = A.u[par] + (size_t)img * G.plane_elems;
     double *__restrict__ uout = (MODE == MODE_KAPPA ? A.kappa_out : A.u[par ^ 1]) + (size_t)img * G.plane_elems;
     const uint8_t *__restrict__ im = A.img + (size_t)img * G.nch * G.plane_elems;
@@ -427,26 +430,26 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
             }
         }
     }
-    if (MODE == MODE_STEP) finish_tile<NCH, false>(A, img, seg, cb, G.ncb_csv, acc, s_red, &s_flag, 0);
+    if (MODE == MODE_STEP) finish_tile<NCH, false>(A, img, seg, cb, G.ncb_csv, acc, 0);
 }
 
 // Sums of the CURRENT level set and of the image: sum a, sum I_k*a, sum I_k, sum mean_k(I)^2.
 // Gives the first step's c1/c2 (src/main.cpp:973-974) and the stop condition (:949-960).
 template <int NCH>
-__global__ void __launch_bounds__(CTA_THREADS, 4) csv_init_kernel(const __grid_constant__ CsvArgs A, int final_mode) {
+__global__ void __launch_bounds__(CTA_THREADS, 8) csv_init_kernel(const __grid_constant__ CsvArgs A, int final_mode) {
     const Geom &G = A.g;
-    __shared__ double s_tab[ATAN_TAB_N];
-    __shared__ double s_red[NACC][CTA_THREADS];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double s_tab[ATAN_TAB_N + 2];
+    const int lane = threadIdx.x;
+    constexpr int warp = 0;
     int bid = blockIdx.x;
     const int cb = bid % G.ncb_csv;
     bid /= G.ncb_csv;
     const int seg = bid % G.nseg;
     const int img = bid / G.nseg;
     CsvState *st = A.state + img;
-    if (tid < ATAN_TAB_N) s_tab[tid] = A.atan_tab[tid];
-    __syncthreads();
+    s_tab[lane] = A.atan_tab[lane];
+    if (lane < ATAN_TAB_N - 32) s_tab[32 + lane] = A.atan_tab[32 + lane];
+    __syncwarp();
     const int par = (final_mode == 1) ? 0 : (st->steps_done & 1);
     const double *__restrict__ uin = A.u[par] + (size_t)img * G.plane_elems;
     const uint8_t *__restrict__ im = A.img + (size_t)img * G.nch * G.plane_elems;
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) csv_init_kernel(const __grid_c
             acc[ACC_SQ] = fma(m1, m1, acc[ACC_SQ]);
         }
     }
-    finish_tile<NCH, true>(A, img, seg, cb, G.ncb_csv, acc, s_red, &s_flag, final_mode);
+    finish_tile<NCH, true>(A, img, seg, cb, G.ncb_csv, acc, final_mode);
 }
 
 // Multi-rank path: after the all-gather of the group sums, one thread per image.

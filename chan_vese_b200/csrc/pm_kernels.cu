@@ -22,6 +22,9 @@ namespace cvb {
 #ifndef PM_PF
 #define PM_PF 8
 #endif
+#ifndef PM_MIN_CTAS
+#define PM_MIN_CTAS 16
+#endif
 
 template <typename T>
 __device__ __forceinline__ double2 pm_load2(const T *p);
@@ -169,10 +172,10 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
 }
 
 template <typename TIN, typename TOUT, bool STRICT>
-__global__ void __launch_bounds__(CTA_THREADS, 4) pm_step_kernel(const __grid_constant__ PmArgs A) {
+__global__ void __launch_bounds__(CTA_THREADS, PM_MIN_CTAS) pm_step_kernel(const __grid_constant__ PmArgs A) {
     const Geom &G = A.g;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the value is warp-uniform
+    const int lane = threadIdx.x;
+    constexpr int warp = 0;
     int bid = blockIdx.x;
     const int cb = bid % G.ncb_pm;
     bid /= G.ncb_pm;

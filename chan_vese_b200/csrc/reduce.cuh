@@ -1,6 +1,6 @@
 // Deterministic fused reductions of the CSV kernels.
 //
-// Every CTA (one row segment x one column block of one image) leaves one partial vector per warp;
+// Every CTA (one warp: one row segment x one column strip of one image) leaves one partial vector;
 // the last CTA of each of the NGROUPS fixed row groups sums that group's partials in a fixed order;
 // the last group finisher adds the NGROUPS group sums in index order and derives c1/c2, the norm and
 // the stop flag.  Groups are keyed to GLOBAL segment indices, so a row-slab run over 1/2/4/8 GPUs
@@ -59,12 +59,14 @@ __device__ inline void csv_finalize_image(const CsvArgs &A, int img, int mode) {
     region_means_from_sums(st, tot, G.nch, (double)G.h * (double)G.w);
 }
 
-// Called by all threads of the CTA after the row loop.  acc holds per-lane sums.
+// Called by the whole warp (= the whole CTA) after the row loop.  acc holds per-lane sums.
+// No block-level barrier anywhere: a CTA is one warp, so warps never wait for one another and a finished warp frees
+// its slot at once.  The last warp of a group adds the group's partial vectors in index order.
 template <int NCH, bool INIT>
 __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, int cb, int ncb, double (&acc)[NACC],
-                                            double (*s_red)[CTA_THREADS], int *s_flag, int final_mode) {
+                                            int final_mode) {
     const Geom &G = A.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
     CsvState *st = A.state + img;
 #pragma unroll
     for (int v = 0; v < NACC; ++v)
@@ -72,53 +74,45 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], off);
         }
-    double *part = A.partials + ((((size_t)img * G.nseg + seg) * ncb + cb) * WARPS_PER_CTA + warp) * NACC;
-    if (lane == 0) {
-#pragma unroll
-        for (int v = 0; v < NACC; ++v)
-            if (slot_used<NCH, INIT>(v)) part[v] = acc[v];
-    }
-    __syncthreads();
+    double *part = A.partials + (((size_t)img * G.nseg + seg) * ncb + cb) * NACC;
     const int gseg = G.seg0 + seg;
     const int grp = (int)(((long long)gseg * NGROUPS) / G.nseg_global);
     // local segments of this group
     const int sb = max(group_seg_begin(grp, G.nseg_global), G.seg0) - G.seg0;
     const int se = min(group_seg_begin(grp + 1, G.nseg_global), G.seg0 + G.nseg) - G.seg0;
-    if (tid == 0) {
+    int last = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < NACC; ++v)
+            if (slot_used<NCH, INIT>(v)) part[v] = acc[v];
         __threadfence();
         const unsigned int old = atomicAdd(&st->group_ticket[grp], 1u);
-        *s_flag = (old == (unsigned int)((se - sb) * ncb) - 1u) ? 1 : 0;
+        last = (old == (unsigned int)((se - sb) * ncb) - 1u) ? 1 : 0;
     }
-    __syncthreads();
-    if (!*s_flag) return;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
     __threadfence();
-    // ---- this CTA finishes group grp: fixed-order sum of its partial vectors
-    const int nvec = (se - sb) * ncb * WARPS_PER_CTA;
-    const double *base = A.partials + (((size_t)img * G.nseg + sb) * ncb * WARPS_PER_CTA) * NACC;
+    // ---- this warp finishes group grp: fixed-order sum of its partial vectors (lane l takes l, l+32, ...)
+    const int nvec = (se - sb) * ncb;
+    const double *base = A.partials + (((size_t)img * G.nseg + sb) * ncb) * NACC;
     double sum[NACC];
 #pragma unroll
     for (int v = 0; v < NACC; ++v) sum[v] = 0.0;
-    for (int i = tid; i < nvec; i += CTA_THREADS) {
+    for (int i = lane; i < nvec; i += 32) {
 #pragma unroll
         for (int v = 0; v < NACC; ++v)
             if (slot_used<NCH, INIT>(v)) sum[v] += ld_cg(base + (size_t)i * NACC + v);
     }
 #pragma unroll
     for (int v = 0; v < NACC; ++v)
-        if (slot_used<NCH, INIT>(v)) s_red[v][tid] = sum[v];
-    __syncthreads();
-    for (int s = CTA_THREADS / 2; s > 0; s >>= 1) {
-        if (tid < s) {
+        if (slot_used<NCH, INIT>(v)) {
 #pragma unroll
-            for (int v = 0; v < NACC; ++v)
-                if (slot_used<NCH, INIT>(v)) s_red[v][tid] += s_red[v][tid + s];
+            for (int off = 16; off > 0; off >>= 1) sum[v] += __shfl_xor_sync(0xffffffffu, sum[v], off);
         }
-        __syncthreads();
-    }
-    if (tid == 0) {
+    if (lane == 0) {
         double *gsum = A.group_sums + ((size_t)grp * G.count + img) * NACC;
 #pragma unroll
-        for (int v = 0; v < NACC; ++v) gsum[v] = slot_used<NCH, INIT>(v) ? s_red[v][0] : 0.0;
+        for (int v = 0; v < NACC; ++v) gsum[v] = slot_used<NCH, INIT>(v) ? sum[v] : 0.0;
         st->group_ticket[grp] = 0u;
         if (!A.multi_rank) {
             __threadfence();
