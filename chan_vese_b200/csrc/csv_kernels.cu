@@ -119,7 +119,7 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
             for (int c = 0; c < NCH; ++c) j1[c] = __ldg(reinterpret_cast<const unsigned short *>(pi + c * pe));
         }
 #endif
-        if (r + CSV_PF < n) {
+        if (CSV_PF > 0 && r + CSV_PF < n) {
             prefetch_l2(pu + (size_t)(CSV_PF - 2) * pitch);
             if (lane < 3 * NCH) prefetch_l2(pi + (size_t)(CSV_PF - 2) * pitch + (lane / 3) * pe + (2 - 2 * lane + (lane % 3) * 31));
         }

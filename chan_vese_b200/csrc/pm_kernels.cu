@@ -138,7 +138,7 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
         const double2 X = q0;  // row i+2
         q0 = q1;
         if (r + 2 < n) q1 = pm_load2<TIN>(pin);
-        if (r + PM_PF < n) prefetch_l2(pin + (size_t)(PM_PF - 2) * pitch);
+        if (PM_PF > 0 && r + PM_PF < n) prefetch_l2(pin + (size_t)(PM_PF - 2) * pitch);
         pin += pitch;
         // g(i+1) from the Sobel sums of rows i, i+1, i+2 (:503-504, :513-522)
         double2 rdC, rsC;

@@ -1,0 +1,90 @@
+"""Row-slab run over N GPUs (torchrun, one process per GPU) against the single-GPU run of the same image:
+PM planes, level set, step count and norm must be BIT-IDENTICAL (fixed reduction groups).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multigpu_check.py [--size 2048]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import chan_vese_b200 as cv  # noqa: E402
+from chan_vese_b200 import synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--csv-steps", type=int, default=12)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    h, w = args.size, args.size - 200
+    ctx = cv.Context(local)
+    rows = cv.auto_tile_rows(h, w, 1)
+    ctx.set_tile_rows(rows)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(ctx.comm_create_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    ctx.comm_init(idt.cpu().numpy().tobytes(), world, rank)
+    lo, hi = cv.slab_partition(h, rows, world, rank)
+    img = synth.hashed_scene_rows(h, w, lo, hi, cell=256, threads=4)
+    prm = cv.make_params(lambda1=[1.0, 0.5, 2.0])
+    with cv.Session(ctx, 3, h, w, rows=(lo, hi)) as s:
+        s.upload_image(img)
+        s.init_checkerboard()
+        n_pm = s.perona_malik(20.0, 0.25, 1.5)
+        pm = s.download_image()
+        steps, norm = s.csv_run(prm, tol=0.0, max_steps=args.csv_steps)
+        u = s.download_levelset()
+        # and an early-stopping run: every rank must stop at the same step
+        s.init_checkerboard()
+        steps2, norm2 = s.csv_run(prm, tol=0.5, max_steps=200)
+        u2 = s.download_levelset()
+    np.save("/tmp/slab_u_%d.npy" % rank, u)
+    np.save("/tmp/slab_u2_%d.npy" % rank, u2)
+    np.save("/tmp/slab_pm_%d.npy" % rank, np.stack(pm))
+    meta = torch.tensor([steps, steps2, n_pm], dtype=torch.int64, device="cuda")
+    allmeta = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(allmeta, meta)
+    dist.barrier()
+    if rank == 0:
+        assert all(torch.equal(m, allmeta[0]) for m in allmeta), allmeta
+        full_u = np.concatenate([np.load("/tmp/slab_u_%d.npy" % r) for r in range(world)])
+        full_u2 = np.concatenate([np.load("/tmp/slab_u2_%d.npy" % r) for r in range(world)])
+        full_pm = np.concatenate([np.load("/tmp/slab_pm_%d.npy" % r) for r in range(world)], axis=1)
+        ctx1 = cv.Context(local)
+        ctx1.set_tile_rows(rows)
+        whole = synth.hashed_scene_rows(h, w, 0, h, cell=256, threads=4)
+        with cv.Session(ctx1, 3, h, w) as s:
+            s.upload_image(whole)
+            s.init_checkerboard()
+            s.perona_malik(20.0, 0.25, 1.5)
+            pm1 = np.stack(s.download_image())
+            st1, nrm1 = s.csv_run(prm, tol=0.0, max_steps=args.csv_steps)
+            u1 = s.download_levelset()
+            s.init_checkerboard()
+            st2, nrm2 = s.csv_run(prm, tol=0.5, max_steps=200)
+            u21 = s.download_levelset()
+        ok = (np.array_equal(full_pm, pm1) and np.array_equal(full_u, u1) and steps == st1 and norm == nrm1 and
+              np.array_equal(full_u2, u21) and steps2 == st2 and norm2 == nrm2)
+        print("MULTIGPU_CHECK world=%d size=%dx%d pm_equal=%s u_equal=%s steps=%d/%d norm_equal=%s early_stop steps=%d/%d u_equal=%s => %s" % (
+            world, h, w, np.array_equal(full_pm, pm1), np.array_equal(full_u, u1), steps, st1, norm == nrm1, steps2, st2,
+            np.array_equal(full_u2, u21), "PASS" if ok else "FAIL"), flush=True)
+        if not ok:
+            d = np.abs(full_u - u1)
+            print("max abs diff", d.max(), "rows with diff", np.unique(np.nonzero(d)[0])[:20])
+    dist.barrier()
+    ctx.comm_destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
