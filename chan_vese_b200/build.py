@@ -50,5 +50,26 @@ def build(force=False, verbose=False, extra_flags=()):
     return LIB_PATH
 
 
+CLI_SRC = os.path.join(os.path.dirname(HERE), "cli", "chan_vese.cpp")
+CLI_BIN = os.path.join(os.path.dirname(HERE), "bin", "chan_vese")
+
+
+def build_cli(force=False):
+    """g++ -std=c++14 host front-end (the reference's bin/chan_vese surface) linked against the C-ABI library."""
+    build()
+    if (not force and os.path.exists(CLI_BIN) and os.path.getmtime(CLI_BIN) >= max(os.path.getmtime(CLI_SRC), os.path.getmtime(HEADER),
+                                                                                    os.path.getmtime(LIB_PATH))):
+        return CLI_BIN
+    os.makedirs(os.path.dirname(CLI_BIN), exist_ok=True)
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-std=c++14", "-O2", "-Wall", "-Wextra", "-I", os.path.dirname(HEADER), "-o", CLI_BIN, CLI_SRC, "-L", LIB_DIR,
+           "-lchan_vese_b200", "-Wl,-rpath," + LIB_DIR]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return CLI_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_cli(force="--force" in sys.argv))
