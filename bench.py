@@ -158,7 +158,7 @@ def run_b200(args):
     h = w = args.size
     stream = torch.cuda.Stream()
     ctx = cv.Context(local, stream=stream.cuda_stream)
-    tile_rows = args.tile_rows or cv.auto_tile_rows(h, w, 1)
+    tile_rows = args.tile_rows or cv.auto_tile_rows(h, w, 1, world)
     ctx.set_tile_rows(tile_rows)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")

@@ -49,7 +49,7 @@ SIGNATURES = {
     "cvb_levelset_checkerboard": (C.c_int, [C.c_int, C.c_int, f64p]),
     "cvb_levelset_rect": (C.c_int, [C.c_int] * 6 + [f64p]),
     "cvb_levelset_circ": (C.c_int, [C.c_int] * 5 + [f64p]),
-    "cvb_auto_tile_rows": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "cvb_auto_tile_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "cvb_slab_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, intp, intp]),
     "cvb_perona_malik": (C.c_int, [vp, u8pp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, u8pp, intp]),
     "cvb_csv_run": (C.c_int, [vp, u8pp, C.c_int, C.c_int, C.c_int, f64p, CsvParamsP, C.c_double, C.c_int, intp, f64p,

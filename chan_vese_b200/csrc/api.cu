@@ -100,6 +100,12 @@ struct Job {
     int ngroups_local = 0;
     int group_lo = 0, group_hi = NGROUPS;  // groups owned by this rank
     bool slab = false;
+    // P2P row-slab run: peers' buffers mapped with CUDA IPC (see comm.cuh / reduce.cuh)
+    bool p2p = false;
+    CommBox *d_box = nullptr;
+    CommView cv{};
+    std::vector<void *> ipc_opened;
+    unsigned int pm_seq = 0;
 };
 struct cvb_session : Job {};
 struct cvb_batch : Job {};
@@ -206,17 +212,49 @@ extern "C" cvb_status cvb_levelset_circ(int h, int w, int cx, int cy, int radius
     return CVB_OK;
 }
 
-static int auto_seg_rows(int h, int w, int count) {
-    const long long target = 2LL * 148 * 20;  // two waves of 20 one-warp CTAs per SM; long segments amortise the row priming
+// Rows per segment.  A CTA is one warp working down one segment of one 64-column strip; the grid is
+// planes x segments x strips CTAs over SLOTS = SMs x resident CTAs per SM slots.  Long segments amortise the row
+// priming (3-4 extra rows and one pipeline fill per CTA), but the LAST wave must be full too: among the candidates
+// pick the one whose wave count wastes the least ("wave quantisation"; at 16384^2 on 8 GPUs 128-row segments give
+// 1.79 waves = 10 % idle, 79-row segments 2.91 waves = 3 %).  Small jobs keep >= 2 waves with at least 4 rows.
+static const int kSlots = 148 * 16;
+static int wave_aware_rows(int rows_per_rank, long long ctas_per_seg) {
+    int best = 0;
+    double best_eff = -1.0;
+    for (int r = 192; r >= 48; --r) {
+        const long long ctas = (long long)ceil_div(rows_per_rank, r) * ctas_per_seg;
+        const double waves = (double)ctas / kSlots;
+        if (waves < 2.0) continue;
+        const double eff = waves / ceil(waves) * (1.0 - 3.5 / (r + 3.5));  // tail loss x priming overhead
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = r;
+        }
+    }
+    return best;
+}
+static int auto_seg_rows(int h, int w, int count, int nranks) {
     const int ncb = ceil_div(w, CSV_CB);
-    const int cands[] = {128, 64, 32, 16, 8, 4};
+    const int rows = ceil_div(h, nranks < 1 ? 1 : nranks);
+    const int r = wave_aware_rows(rows, (long long)count * ncb);
+    if (r > 0) return r;
+    const int cands[] = {32, 16, 8, 4};
     for (int s : cands)
-        if ((long long)count * ceil_div(h, s) * ncb >= target) return s;
+        if ((long long)count * ceil_div(rows, s) * ncb >= 2LL * kSlots) return s;
     return 4;
 }
-extern "C" int cvb_auto_tile_rows(int h, int w, int count) {
-    if (h <= 0 || w <= 0 || count <= 0) return 0;
-    return auto_seg_rows(h, w, count);
+static int auto_pm_seg_rows(int rows, int w, int planes) {
+    const int ncb = ceil_div(w, PM_CB);
+    const int r = wave_aware_rows(rows, (long long)planes * ncb);
+    if (r > 0) return r;
+    const int cands[] = {32, 16, 8, 4};
+    for (int s : cands)
+        if ((long long)planes * ceil_div(rows, s) * ncb >= 2LL * kSlots) return s;
+    return 4;
+}
+extern "C" int cvb_auto_tile_rows(int h, int w, int count, int nranks) {
+    if (h <= 0 || w <= 0 || count <= 0 || nranks <= 0) return 0;
+    return auto_seg_rows(h, w, count, nranks);
 }
 extern "C" cvb_status cvb_slab_partition(int h, int tile_rows, int nranks, int rank, int *row_lo, int *row_hi) {
     if (h <= 0 || tile_rows <= 0 || nranks <= 0 || rank < 0 || rank >= nranks || NGROUPS % nranks != 0 || !row_lo ||
@@ -393,6 +431,16 @@ static void job_free(Job *j) {
     cudaFree(j->d_partials);
     cudaFree(j->d_group);
     cudaFree(j->d_sign);
+    if (!j->ipc_opened.empty()) {
+        for (void *p : j->ipc_opened) cudaIpcCloseMemHandle(p);
+        j->ipc_opened.clear();
+        // nobody frees a buffer a peer may still have mapped: a tiny all-gather is the barrier
+        if (j->ctx->comm && j->d_box && g_nccl.AllGather) {
+            g_nccl.AllGather(reinterpret_cast<char *>(j->d_box) + j->ctx->rank, j->d_box, 1, ncclUint8, j->ctx->comm, j->ctx->stream);
+            cudaStreamSynchronize(j->ctx->stream);
+        }
+    }
+    cudaFree(j->d_box);
     if (j->h_state) cudaFreeHost(j->h_state);
 }
 
@@ -417,7 +465,7 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     g.rows_alloc = row_hi - row_lo + 2 * HALO;
     g.nch = n;
     g.count = count;
-    g.seg_rows = c->tile_rows > 0 ? c->tile_rows : auto_seg_rows(h, w, count);
+    g.seg_rows = c->tile_rows > 0 ? c->tile_rows : auto_seg_rows(h, w, count, slab ? c->nranks : 1);
     g.nseg_global = ceil_div(h, g.seg_rows);
     if (row_lo % g.seg_rows != 0 || (row_hi != h && row_hi % g.seg_rows != 0))
         return fail(c, CVB_ERR_INVALID_ARGUMENT, "slab rows [%d,%d) are not aligned to tile_rows=%d (use cvb_slab_partition)",
@@ -426,8 +474,11 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     g.nseg = ceil_div(row_hi, g.seg_rows) - g.seg0;
     g.ncb_csv = ceil_div(w, CSV_CB);
     g.ncb_pm = ceil_div(w, PM_CB);
+    // PM has no reductions, so its segments need not follow the reduction groups: own wave-aware segment length
+    g.pm_seg_rows = auto_pm_seg_rows(row_hi - row_lo, w, count * n);
+    g.pm_nseg = ceil_div(row_hi - row_lo, g.pm_seg_rows);
     g.plane_elems = (long long)g.rows_alloc * g.pitch;
-    if ((long long)count * n * g.nseg * std::max(g.ncb_csv, g.ncb_pm) > 0x7fffffffLL)
+    if ((long long)count * n * std::max(g.nseg, g.pm_nseg) * std::max(g.ncb_csv, g.ncb_pm) > 0x7fffffffLL)
         return fail(c, CVB_ERR_INVALID_ARGUMENT, "job too large for one launch");
     // groups owned by this job
     j->ngroups_local = 0;
@@ -453,14 +504,14 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     CU(c, cudaMalloc(&j->d_state, (size_t)count * sizeof(CsvState)));
     const size_t npart = (size_t)count * g.nseg * g.ncb_csv * WARPS_PER_CTA * NACC;
     CU(c, cudaMalloc(&j->d_partials, npart * sizeof(double)));
-    CU(c, cudaMalloc(&j->d_group, (size_t)NGROUPS * count * NACC * sizeof(double)));
+    CU(c, cudaMalloc(&j->d_group, 2 * (size_t)NGROUPS * count * NACC * sizeof(double)));
     CU(c, cudaMallocHost(&j->h_state, 2 * (size_t)count * sizeof(CsvState)));
     CU(c, cudaMemsetAsync(j->d_img, 0, (size_t)count * n * pe, c->stream));
     CU(c, cudaMemsetAsync(j->d_u[0], 0, (size_t)count * pe * sizeof(double), c->stream));
     CU(c, cudaMemsetAsync(j->d_u[1], 0, (size_t)count * pe * sizeof(double), c->stream));
     CU(c, cudaMemsetAsync(j->d_state, 0, (size_t)count * sizeof(CsvState), c->stream));
     CU(c, cudaMemsetAsync(j->d_partials, 0, npart * sizeof(double), c->stream));
-    CU(c, cudaMemsetAsync(j->d_group, 0, (size_t)NGROUPS * count * NACC * sizeof(double), c->stream));
+    CU(c, cudaMemsetAsync(j->d_group, 0, 2 * (size_t)NGROUPS * count * NACC * sizeof(double), c->stream));
     return CVB_OK;
 }
 
@@ -490,13 +541,21 @@ static void fill_args(const Job *j, const cvb_csv_params *p, double tol, CsvArgs
     A.tol = tol;
     A.multi_rank = (j->slab && j->ctx->nranks > 1) ? 1 : 0;
     A.ngroups_local = j->ngroups_local;
+    A.group_lo = j->group_lo;
+    A.group_hi = j->group_hi;
     A.g = j->g;
+    A.cv = j->cv;  // p2p == 0 unless the slab session mapped its peers
 }
 
 // all-gather of the group sums + finalize (multi-rank only)
 static cvb_status reduce_across_ranks(Job *j, const CsvArgs &A, int mode) {
     cvb_context *c = j->ctx;
     if (!A.multi_rank) return CVB_OK;
+    if (j->p2p) {  // the kernel pushed its group sums to the peers: one warp waits for all ranks and folds
+        CU(c, launch_csv_finalize(A, mode, c->stream));
+        c->stats.kernel_launches += 1;
+        return CVB_OK;
+    }
     const size_t per_rank = (size_t)(NGROUPS / c->nranks) * j->g.count * NACC;
     NC(c, g_nccl.AllGather(j->d_group + per_rank * c->rank, j->d_group, per_rank, ncclFloat64, c->comm, c->stream));
     CU(c, launch_csv_finalize(A, mode, c->stream));
@@ -655,21 +714,33 @@ static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *st
         }
     const bool strict = c->math == CVB_MATH_STRICT;
     PmArgs A;
+    memset(&A, 0, sizeof A);
     A.K = K;
     A.L = L;
     A.inv_k2 = 1.0 / (K * K);
     A.g = g;
+    A.cv = j->cv;
     CU(c, cudaEventRecord(c->ev[0], c->stream));
     for (int s = 1; s <= nsteps; ++s) {
         const bool first = s == 1, last = s == nsteps && nsteps >= 2;
         A.in = first ? (const void *)j->d_img : (const void *)j->d_pm[(s - 2) & 1];
         A.out = last ? (void *)j->d_img : (void *)j->d_pm[(s - 1) & 1];
+        A.out_buf = last ? -1 : ((s - 1) & 1);
+        if (j->p2p) {
+            // boundary rows travel inside the kernel (stores into the neighbours' halos + a flag); before a launch
+            // that READS pushed rows, one warp waits for both neighbours' flags of the previous launch
+            if (!first) {
+                CU(c, launch_pm_wait(j->d_box, j->pm_seq, c->rank > 0, c->rank < c->nranks - 1, c->stream));
+                c->stats.kernel_launches += 1;
+            }
+            A.cv.pm_seq = ++j->pm_seq;
+        }
         CU(c, launch_pm_step(A, first, last, strict, c->stream));
         c->stats.kernel_launches += 1;
         c->stats.pm_step_launches += 1;
         if (last)
             TRY(exchange_halo(j, j->d_img, 1, nplanes));
-        else if (s < nsteps)
+        else if (s < nsteps && !j->p2p)
             TRY(exchange_halo(j, j->d_pm[(s - 1) & 1], sizeof(double), nplanes));
     }
     if (nsteps == 1) {  // u8 -> fp64 -> u8: the single step cannot write the plane it reads
@@ -712,7 +783,7 @@ static cvb_status job_csv_launch_step(Job *j, const CsvArgs &A, int step_index /
     c->stats.csv_step_launches += 1;
     if (A.multi_rank) {
         TRY(reduce_across_ranks(j, A, 0));
-        TRY(exchange_halo(j, j->d_u[(step_index + 1) & 1], sizeof(double), j->g.count));
+        if (!j->p2p) TRY(exchange_halo(j, j->d_u[(step_index + 1) & 1], sizeof(double), j->g.count));
     }
     return CVB_OK;
 }
@@ -827,6 +898,85 @@ static cvb_status job_csv_step(Job *j, const cvb_csv_params *p, const double *c1
     return CVB_OK;
 }
 
+// Map the peers' buffers of a slab session (CUDA IPC over NVLink).  Collective: every rank calls it for its slab.
+struct IpcRecord {
+    cudaIpcMemHandle_t u[2], pm[2], group, box;
+    int rows;
+    int pad[3];
+};
+static cvb_status job_setup_p2p(Job *j) {
+    cvb_context *c = j->ctx;
+    const Geom &g = j->g;
+    const char *mode = getenv("CVB_COMM");
+    if (mode && strcmp(mode, "nccl") == 0) return CVB_OK;  // keep NCCL in the step loop (comparison / fallback)
+    if (c->nranks > MAX_RANKS) return CVB_OK;
+    const int nplanes = g.count * g.nch;
+    const size_t pm_bytes = (size_t)nplanes * g.plane_elems * sizeof(double);
+    for (int b = 0; b < 2; ++b)
+        if (!j->d_pm[b]) {
+            CU(c, cudaMalloc(&j->d_pm[b], pm_bytes));
+            CU(c, cudaMemsetAsync(j->d_pm[b], 0, pm_bytes, c->stream));
+        }
+    CU(c, cudaMalloc(&j->d_box, sizeof(CommBox)));
+    CU(c, cudaMemsetAsync(j->d_box, 0, sizeof(CommBox), c->stream));
+    IpcRecord mine;
+    memset(&mine, 0, sizeof mine);
+    CU(c, cudaIpcGetMemHandle(&mine.u[0], j->d_u[0]));
+    CU(c, cudaIpcGetMemHandle(&mine.u[1], j->d_u[1]));
+    CU(c, cudaIpcGetMemHandle(&mine.pm[0], j->d_pm[0]));
+    CU(c, cudaIpcGetMemHandle(&mine.pm[1], j->d_pm[1]));
+    CU(c, cudaIpcGetMemHandle(&mine.group, j->d_group));
+    CU(c, cudaIpcGetMemHandle(&mine.box, j->d_box));
+    mine.rows = g.row_hi - g.row_lo;
+    // all-gather the records through the communicator that already exists
+    IpcRecord *d_rec = nullptr;
+    CU(c, cudaMalloc(&d_rec, sizeof(IpcRecord) * c->nranks));
+    CU(c, cudaMemcpyAsync(d_rec + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    NC(c, g_nccl.AllGather(d_rec + c->rank, d_rec, sizeof(IpcRecord), ncclUint8, c->comm, c->stream));
+    std::vector<IpcRecord> all(c->nranks);
+    CU(c, cudaMemcpyAsync(all.data(), d_rec, sizeof(IpcRecord) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_rec);
+    CommView &v = j->cv;
+    memset(&v, 0, sizeof v);
+    v.nranks = c->nranks;
+    v.rank = c->rank;
+    v.box = j->d_box;
+    auto open = [&](const cudaIpcMemHandle_t &h, void **out) -> cudaError_t {
+        cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) j->ipc_opened.push_back(*out);
+        return e;
+    };
+    for (int p = 0; p < c->nranks; ++p) {
+        if (p == c->rank) {
+            v.peer_box[p] = j->d_box;
+            v.peer_group[p] = j->d_group;
+            continue;
+        }
+        CU(c, open(all[p].box, (void **)&v.peer_box[p]));
+        CU(c, open(all[p].group, (void **)&v.peer_group[p]));
+    }
+    if (c->rank > 0) {
+        const IpcRecord &r = all[c->rank - 1];
+        v.up_rows = r.rows;
+        for (int b = 0; b < 2; ++b) {
+            CU(c, open(r.u[b], (void **)&v.up_u[b]));
+            CU(c, open(r.pm[b], (void **)&v.up_pm[b]));
+        }
+    }
+    if (c->rank < c->nranks - 1) {
+        const IpcRecord &r = all[c->rank + 1];
+        v.dn_rows = r.rows;
+        for (int b = 0; b < 2; ++b) {
+            CU(c, open(r.u[b], (void **)&v.dn_u[b]));
+            CU(c, open(r.pm[b], (void **)&v.dn_pm[b]));
+        }
+    }
+    v.p2p = 1;
+    j->p2p = true;
+    return CVB_OK;
+}
+
 // ---- sessions --------------------------------------------------------------------------------------------------
 extern "C" cvb_status cvb_session_create_slab(cvb_context *c, int n, int h, int w, int row_lo, int row_hi,
                                               cvb_precision prec, cvb_session **out) {
@@ -847,6 +997,12 @@ extern "C" cvb_status cvb_session_create_slab(cvb_context *c, int n, int h, int 
             job_free(s);
             delete s;
             return fail(c, CVB_ERR_INVALID_ARGUMENT, "slab rows do not match rank %d of %d (use cvb_slab_partition)", c->rank, c->nranks);
+        }
+        st = job_setup_p2p(s);
+        if (st != CVB_OK) {
+            job_free(s);
+            delete s;
+            return st;
         }
     }
     *out = s;

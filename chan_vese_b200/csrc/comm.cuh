@@ -1,0 +1,39 @@
+// Device side of the NCCL-free multi-GPU step loop: release/acquire flags in peer memory over NVLink.
+//
+// Row-slab protocol (one process per GPU, peers' buffers mapped with CUDA IPC):
+//   * a CTA that writes one of the slab's first/last HALO rows also stores it into the neighbour's halo rows;
+//   * the warp that completes the last local reduction group copies this rank's group sums into every peer's
+//     group-sum array and then bumps arrive[rank] in every peer's CommBox (st.release.sys after a system fence);
+//   * the NEXT launch starts by folding the newest reduction: the first warp to get there waits until all ranks
+//     have arrived, adds the 32 group sums in index order (identical on every rank => bit-identical c1/c2 and stop
+//     decision everywhere), publishes `finalized`; every other warp waits for that before touching c1/c2 or halo rows.
+// Nothing ever waits for a kernel on the SAME GPU that might not be resident: the folding warp is elected among
+// the warps that are running, and peers only wait for the previous launch of their neighbours.
+#pragma once
+#include "common.cuh"
+
+namespace cvb {
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+}  // namespace cvb

@@ -43,6 +43,7 @@ struct Geom {
     int seg0;            // global index of the first local segment (row_lo / seg_rows)
     int nseg_global;     // segments of the whole image
     int ncb_csv, ncb_pm; // column blocks (CTAs per segment)
+    int pm_seg_rows, pm_nseg;  // PM segments: [row_lo + s*pm_seg_rows, ...) (PM has no reduction groups to follow)
     long long plane_elems;  // rows_alloc * pitch
 };
 
@@ -61,12 +62,37 @@ struct CsvState {
     int pad;
 };
 
+// ---- multi-GPU row slabs without NCCL in the step loop: peers' memory mapped through CUDA IPC (NVLink) -----------
+constexpr int MAX_RANKS = 8;
+// One per slab session, in device memory that the peers can write.  All counters only ever grow.
+struct CommBox {
+    unsigned int arrive[MAX_RANKS];  // arrive[p] = number of reductions whose group sums rank p has pushed to me
+    unsigned int produced;           // reductions my own kernels have produced (and pushed)
+    unsigned int finalized;          // reductions folded into CsvState (c1/c2, norm, stop flag)
+    unsigned int claimed;            // leader election for the next fold
+    int pending_mode;                // csv_finalize_image mode of the newest produced reduction
+    unsigned int pm_from_above;      // PM launches whose boundary rows the upper neighbour has pushed into my top halo
+    unsigned int pm_from_below;
+    unsigned int pm_ticket_up, pm_ticket_dn;  // boundary CTAs of the running PM launch that have finished
+};
+struct CommView {
+    int p2p;                         // 0: NCCL path (all-gather + send/recv issued by the host between launches)
+    int nranks, rank;
+    int up_rows, dn_rows;            // rows owned by the neighbours (upper: its bottom halo starts at local row HALO+up_rows)
+    unsigned int pm_seq;             // sequence number of this PM launch; boundary CTAs wait for pm_seq-1 (0: no wait)
+    CommBox *box;                    // mine
+    CommBox *peer_box[MAX_RANKS];    // peer_box[rank] == box
+    double *peer_group[MAX_RANKS];   // peers' (double-buffered) group-sum arrays
+    double *up_u[2], *dn_u[2];       // neighbours' level-set ping-pong buffers (nullptr at the image border)
+    double *up_pm[2], *dn_pm[2];     // neighbours' PM state buffers
+};
+
 struct CsvArgs {
     double *u[2];           // ping-pong level-set buffers, count planes each
     const uint8_t *img;     // count * nch planes
     CsvState *state;        // count
     double *partials;       // [count][nseg][ncb][NACC]
-    double *group_sums;     // [NGROUPS][count][NACC]
+    double *group_sums;     // [2][NGROUPS][count][NACC] (second copy: P2P double buffering)
     double *kappa_out;      // MODE_KAPPA only
     const double *atan_tab; // 34 entries, see math.cuh
     double alpha, beta, gamma;  // mu*dt, (1/N)*dt, -nu*dt (src/main.cpp:985 as one addWeighted)
@@ -75,14 +101,18 @@ struct CsvArgs {
     double tol;
     int multi_rank;         // 1: stop after the group sums; csv_finalize runs after the all-gather
     int ngroups_local;      // non-empty groups owned by this rank
+    int group_lo, group_hi; // groups owned by this rank
     Geom g;
+    CommView cv;
 };
 
 struct PmArgs {
     const void *in;   // double* or uint8_t* (first step), count*nch planes
     void *out;        // double* or uint8_t* (last step)
     double K, L, inv_k2;
+    int out_buf;      // index of the PM state buffer being written (for the neighbour pushes), -1: uint8 output
     Geom g;
+    CommView cv;
 };
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

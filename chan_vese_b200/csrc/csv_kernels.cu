@@ -26,7 +26,7 @@ namespace cvb {
 #define CSV_PF 8
 #endif
 #ifndef CSV_MIN_CTAS
-#define CSV_MIN_CTAS 20  // one-warp CTAs: 20 resident warps per SM = 96 registers per thread
+#define CSV_MIN_CTAS 16  // one-warp CTAs: 16 resident warps per SM = 128 registers per thread (more did not help)
 #endif
 #ifndef CSV_NO_UNIFORM_COEF
 #define CSV_UNIFORM_COEF 1
@@ -34,6 +34,43 @@ namespace cvb {
 
 enum { MODE_STEP = 0, MODE_KAPPA = 1 };
 
+
+// P2P multi-GPU: rows that are a neighbouring slab's halo are also stored straight into that neighbour's buffer.
+__device__ __forceinline__ bool push_halo_rows(const CsvArgs &A, int buf, int i, int a, int lane, double v0, double v1) {
+    const Geom &G = A.g;
+    bool pushed = false;
+    if (i < G.row_lo + HALO && A.cv.up_u[buf] != nullptr) {
+        double *d = A.cv.up_u[buf] + (size_t)(HALO + A.cv.up_rows + (i - G.row_lo)) * G.pitch + a;
+        if (lane >= 1 && a + 1 < G.w)
+            *reinterpret_cast<double2 *>(d) = make_double2(v0, v1);
+        else if (lane >= 1 && a < G.w)
+            *d = v0;
+        pushed = true;
+    }
+    if (i >= G.row_hi - HALO && A.cv.dn_u[buf] != nullptr) {
+        double *d = A.cv.dn_u[buf] + (size_t)(i - (G.row_hi - HALO)) * G.pitch + a;
+        if (lane >= 1 && a + 1 < G.w)
+            *reinterpret_cast<double2 *>(d) = make_double2(v0, v1);
+        else if (lane >= 1 && a < G.w)
+            *d = v0;
+        pushed = true;
+    }
+    return pushed;
+}
+
+// Read back the boundary rows this warp just wrote (L2 hits) and store them straight into the neighbour's buffer --
+// outside the hot loop, and out of line so that the hot loop's register allocation does not see it.
+__device__ __noinline__ bool push_boundary_rows(const CsvArgs &A, const double *uout, int buf, int ra, int rb, int a, int lane) {
+    const Geom &G = A.g;
+    bool pushed = false;
+    const int lo_end = min(rb, G.row_lo + HALO), hi_beg = max(ra, G.row_hi - HALO);
+    for (int i = ra; i < rb; ++i) {
+        if (i >= lo_end && i < hi_beg) continue;
+        const double2 v = __ldcg(reinterpret_cast<const double2 *>(uout + (size_t)(i - G.row_lo + HALO) * G.pitch + a));
+        pushed |= push_halo_rows(A, buf, i, a, lane, v.x, v.y);
+    }
+    return pushed;
+}
 
 // Coefficients of one step, derived from the region means once per thread.
 template <int NCH>
@@ -158,6 +195,7 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
         const double un0 = C.x + du0, un1 = C.y + du1;
         if (lane) *reinterpret_cast<double2 *>(po) = make_double2(un0, un1);
         po += pitch;
+
         // sums of the updated level set and of du^2 (lane 0 is a halo lane: its sums are dropped at the end)
         const double a0 = atan_over_pi(un0 * K.inv_eps, s_tab);
         const double a1 = atan_over_pi(un1 * K.inv_eps, s_tab);
@@ -198,9 +236,9 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     const int seg = bid % G.nseg;
     const int img = bid / G.nseg;
     CsvState *st = A.state + img;
-    const int2 ds = *reinterpret_cast<const int2 *>(&st->done);  // {done, steps_done}
     s_tab[lane] = A.atan_tab[lane];
     if (lane < ATAN_TAB_N - 32) s_tab[32 + lane] = A.atan_tab[32 + lane];
+    const int2 ds = *reinterpret_cast<const int2 *>(&st->done);  // {done, steps_done}
     if (MODE == MODE_STEP && ds.x) return;  // frozen image: the launch is a no-op (src/main.cpp:1000)
     __syncwarp();
 
@@ -402,6 +440,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
                                     *reinterpret_cast<double2 *>(uout + offo) = make_double2(un0, un1);
                                 else if (v0)
                                     uout[offo] = un0;
+
                                 // sums of the UPDATED level set (next step's c1/c2) and of du^2 (:993)
                                 double a0 = atan_over_pi(un0 * inv_eps, s_tab);
                                 double a1 = atan_over_pi(un1 * inv_eps, s_tab);
@@ -430,7 +469,13 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
             }
         }
     }
-    if (MODE == MODE_STEP) finish_tile<NCH, false>(A, img, seg, cb, G.ncb_csv, acc, 0);
+    if (MODE == MODE_STEP) {
+        // P2P multi-GPU: the slab's first / last HALO rows are the neighbours' halo rows
+        bool pushed = false;
+        if (A.cv.p2p && cs < w && colok && (ra < G.row_lo + HALO || rb > G.row_hi - HALO))
+            pushed = push_boundary_rows(A, uout, par ^ 1, ra, rb, a, lane);
+        finish_tile<NCH, false>(A, img, seg, cb, G.ncb_csv, acc, 0, pushed);
+    }
 }
 
 // Sums of the CURRENT level set and of the image: sum a, sum I_k*a, sum I_k, sum mean_k(I)^2.
@@ -498,10 +543,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) csv_init_kernel(const __grid_c
 
 // Multi-rank path: after the all-gather of the group sums, one thread per image.
 __global__ void csv_finalize_kernel(const __grid_constant__ CsvArgs A, int mode) {
-    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (A.cv.p2p) {  // P2P: one warp waits for every rank's group sums of the newest reduction and folds them
+        csv_wait_fold(A);
+        return;
+    }
+    // NCCL path: the host all-gathered the group sums; one warp per image folds them
+    const int img = blockIdx.x;
     if (img >= A.g.count) return;
     if (mode == 0 && A.state[img].done) return;
-    csv_finalize_image(A, img, mode);
+    csv_fold(A, img, mode, 0u);
 }
 
 // ---- elementwise helpers ------------------------------------------------------------------------------
@@ -569,7 +619,7 @@ cudaError_t launch_csv_init(const CsvArgs &A, int final_mode, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t launch_csv_finalize(const CsvArgs &A, int mode, cudaStream_t s) {
-    csv_finalize_kernel<<<(A.g.count + 127) / 128, 128, 0, s>>>(A, mode);
+    csv_finalize_kernel<<<A.g.count, 32, 0, s>>>(A, mode);
     return cudaGetLastError();
 }
 cudaError_t launch_delta_map(double *data, size_t n, double eps, cudaStream_t s) {

@@ -10,6 +10,7 @@
 // of I, three rows of the separable Sobel row sums and three rows of g live in registers; west/east
 // neighbours come from warp shuffles.  The stencil has radius 2, so lanes 0 and 31 are halo lanes:
 // a strip owns 60 columns, a 4-warp CTA 240.
+#include "comm.cuh"
 #include "common.cuh"
 #include "kernels.h"
 #include "math.cuh"
@@ -172,32 +173,10 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
 }
 
 template <typename TIN, typename TOUT, bool STRICT>
-__global__ void __launch_bounds__(CTA_THREADS, PM_MIN_CTAS) pm_step_kernel(const __grid_constant__ PmArgs A) {
-    const Geom &G = A.g;
-    const int lane = threadIdx.x;
-    constexpr int warp = 0;
-    int bid = blockIdx.x;
-    const int cb = bid % G.ncb_pm;
-    bid /= G.ncb_pm;
-    const int seg = bid % G.nseg;
-    const int plane = bid / G.nseg;  // image * nch + channel: channels diffuse independently (:489)
-    const TIN *__restrict__ in = reinterpret_cast<const TIN *>(A.in) + (size_t)plane * G.plane_elems;
-    TOUT *__restrict__ out = reinterpret_cast<TOUT *>(A.out) + (size_t)plane * G.plane_elems;
-    const int gseg = G.seg0 + seg;
-    const int ra = max(gseg * G.seg_rows, G.row_lo);
-    const int rb = min((gseg + 1) * G.seg_rows, G.row_hi);
-    const int cs = cb * PM_CB + warp * PM_STRIP_OWN;
-    if (cs >= G.w) return;
-    const int a = cs - 2 + 2 * lane;
+__device__ __forceinline__ void pm_rows_generic(const TIN *__restrict__ in, TOUT *__restrict__ out, const Geom &G, int ra,
+                                                int rb, int a, int lane, bool colok, double K, double L, double inv_k2,
+                                                double lq) {
     const int w = G.w, h = G.h;
-    const bool colok = a >= 0 && a < G.pitch;
-    const double K = A.K, L = A.L;
-    const double inv_k2 = A.inv_k2, lq = L * 0.25;
-    // CTAs whose stencils stay inside the image take the fast path (all but the outermost ring)
-    if (!STRICT && cb >= 1 && (cb + 1) * PM_CB + 2 <= w && ra >= 2 && rb <= h - 2) {
-        pm_rows_fast<TIN, TOUT>(in, out, G, ra, rb, a, lane, inv_k2, lq);
-        return;
-    }
 
     const int nk = rb - ra + 4;  // streamed rows ra-2 .. rb+1
     auto row_off = [&](int k) -> size_t {
@@ -277,6 +256,98 @@ __global__ void __launch_bounds__(CTA_THREADS, PM_MIN_CTAS) pm_step_kernel(const
     }
 }
 
+// P2P multi-GPU: the slab's first / last HALO rows are the neighbours' halo rows.  Read back what this warp just
+// wrote and store it into the neighbour's output buffer; the LAST boundary CTA of the launch then raises the
+// neighbour's flag (st.release.sys after system fences), which pm_wait_kernel polls before the next launch.
+template <typename TOUT>
+__device__ __noinline__ void pm_push_boundary(const PmArgs &A, const TOUT *out, int plane, int ra, int rb, int a, int lane) {
+    const Geom &G = A.g;
+    const bool top = ra < G.row_lo + HALO && A.cv.rank > 0, bot = rb > G.row_hi - HALO && A.cv.rank < A.cv.nranks - 1;
+    if (!top && !bot) return;
+    if (sizeof(TOUT) == 8 && A.out_buf >= 0 && lane >= 1 && lane <= 30 && a < G.w) {
+        const double *o = reinterpret_cast<const double *>(out);
+        for (int i = ra; i < rb; ++i) {
+            const bool t = top && i < G.row_lo + HALO, b = bot && i >= G.row_hi - HALO;
+            if (!t && !b) continue;
+            const double *src = o + (size_t)(i - G.row_lo + HALO) * G.pitch + a;
+            const bool two = a + 1 < G.w;
+            const double v0 = __ldcg(src), v1 = two ? __ldcg(src + 1) : 0.0;
+            if (t) {
+                double *d = A.cv.up_pm[A.out_buf] + (size_t)plane * (size_t)(A.cv.up_rows + 2 * HALO) * G.pitch +
+                            (size_t)(HALO + A.cv.up_rows + (i - G.row_lo)) * G.pitch + a;
+                pm_store(d, v0, v1, two);
+            }
+            if (b) {
+                double *d = A.cv.dn_pm[A.out_buf] + (size_t)plane * (size_t)(A.cv.dn_rows + 2 * HALO) * G.pitch +
+                            (size_t)(i - (G.row_hi - HALO)) * G.pitch + a;
+                pm_store(d, v0, v1, two);
+            }
+        }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned int nb = (unsigned int)(G.ncb_pm * G.count * G.nch);  // boundary CTAs per side
+        if (top) {
+            __threadfence();
+            if (atomicAdd(&A.cv.box->pm_ticket_up, 1u) == nb - 1u) {
+                A.cv.box->pm_ticket_up = 0u;
+                __threadfence_system();
+                st_release_sys(&A.cv.peer_box[A.cv.rank - 1]->pm_from_below, A.cv.pm_seq);
+            }
+        }
+        if (bot) {
+            __threadfence();
+            if (atomicAdd(&A.cv.box->pm_ticket_dn, 1u) == nb - 1u) {
+                A.cv.box->pm_ticket_dn = 0u;
+                __threadfence_system();
+                st_release_sys(&A.cv.peer_box[A.cv.rank + 1]->pm_from_above, A.cv.pm_seq);
+            }
+        }
+    }
+}
+
+// One warp, between two PM launches of a P2P slab run: wait until both neighbours have pushed launch `need`.
+__global__ void pm_wait_kernel(const CommBox *box, unsigned int need, int has_up, int has_dn) {
+    if (threadIdx.x == 0 && has_up)
+        while (ld_acquire_sys(&box->pm_from_above) < need) {
+        }
+    if (threadIdx.x == 1 && has_dn)
+        while (ld_acquire_sys(&box->pm_from_below) < need) {
+        }
+}
+
+template <typename TIN, typename TOUT, bool STRICT>
+__global__ void __launch_bounds__(CTA_THREADS, PM_MIN_CTAS) pm_step_kernel(const __grid_constant__ PmArgs A) {
+    const Geom &G = A.g;
+    const int lane = threadIdx.x;
+    constexpr int warp = 0;
+    int bid = blockIdx.x;
+    const int cb = bid % G.ncb_pm;
+    bid /= G.ncb_pm;
+    const int seg = bid % G.pm_nseg;
+    const int plane = bid / G.pm_nseg;  // image * nch + channel: channels diffuse independently (:489)
+    const TIN *__restrict__ in = reinterpret_cast<const TIN *>(A.in) + (size_t)plane * G.plane_elems;
+    TOUT *__restrict__ out = reinterpret_cast<TOUT *>(A.out) + (size_t)plane * G.plane_elems;
+    const int ra = G.row_lo + seg * G.pm_seg_rows;
+    const int rb = min(ra + G.pm_seg_rows, G.row_hi);
+    const int cs = cb * PM_CB + warp * PM_STRIP_OWN;
+    if (cs >= G.w) return;
+    const int a = cs - 2 + 2 * lane;
+    const int w = G.w, h = G.h;
+    const bool colok = a >= 0 && a < G.pitch;
+    const double K = A.K, L = A.L;
+    const double inv_k2 = A.inv_k2, lq = L * 0.25;
+    // CTAs whose stencils stay inside the image take the fast path (all but the outermost ring)
+    const bool interior = !STRICT && cb >= 1 && (cb + 1) * PM_CB + 2 <= w && ra >= 2 && rb <= h - 2;
+    if (interior) {
+        pm_rows_fast<TIN, TOUT>(in, out, G, ra, rb, a, lane, inv_k2, lq);
+    } else {
+        pm_rows_generic<TIN, TOUT, STRICT>(in, out, G, ra, rb, a, lane, colok, K, L, inv_k2, lq);
+    }
+    if (A.cv.p2p) pm_push_boundary<TOUT>(A, out, plane, ra, rb, a, lane);
+}
+
 __global__ void pm_quantise_kernel(const double *in, uint8_t *out, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) out[q] = (uint8_t)sat_u8(in[q]);
@@ -285,7 +356,7 @@ __global__ void pm_quantise_kernel(const double *in, uint8_t *out, size_t n) {
 template <typename TIN, typename TOUT>
 static cudaError_t launch_pm_t(const PmArgs &A, bool strict, cudaStream_t s) {
     const Geom &G = A.g;
-    const unsigned int grid = (unsigned int)((size_t)G.count * G.nch * G.nseg * G.ncb_pm);
+    const unsigned int grid = (unsigned int)((size_t)G.count * G.nch * G.pm_nseg * G.ncb_pm);
     if (strict)
         pm_step_kernel<TIN, TOUT, true><<<grid, CTA_THREADS, 0, s>>>(A);
     else
@@ -298,6 +369,11 @@ cudaError_t launch_pm_step(const PmArgs &A, bool in_u8, bool out_u8, bool strict
     if (in_u8) return launch_pm_t<uint8_t, double>(A, strict, s);
     if (out_u8) return launch_pm_t<double, uint8_t>(A, strict, s);
     return launch_pm_t<double, double>(A, strict, s);
+}
+
+cudaError_t launch_pm_wait(const CommBox *box, unsigned int need, int has_up, int has_dn, cudaStream_t s) {
+    pm_wait_kernel<<<1, 32, 0, s>>>(box, need, has_up, has_dn);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_pm_quantise(const double *in, uint8_t *out, size_t n, cudaStream_t s) {

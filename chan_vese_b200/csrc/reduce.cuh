@@ -1,12 +1,18 @@
-// Deterministic fused reductions of the CSV kernels.
+// Deterministic fused reductions of the CSV kernels, single- and multi-GPU.
 //
-// Every CTA (one warp: one row segment x one column strip of one image) leaves one partial vector;
-// the last CTA of each of the NGROUPS fixed row groups sums that group's partials in a fixed order;
-// the last group finisher adds the NGROUPS group sums in index order and derives c1/c2, the norm and
-// the stop flag.  Groups are keyed to GLOBAL segment indices, so a row-slab run over 1/2/4/8 GPUs
-// (each rank owning NGROUPS/G consecutive groups, the group sums all-gathered) adds exactly the same
-// numbers in exactly the same order as the single-GPU run.  No floating-point atomics anywhere.
+// Every CTA (one warp: one row segment x one column strip of one image) leaves one partial vector; the last CTA of
+// each of the NGROUPS fixed row groups sums that group's partials in a fixed order ("group sums"); the warp that
+// completes the last LOCAL group either
+//   * single GPU: FOLDS the reduction at once -- adds the NGROUPS group sums with a fixed shuffle tree (lane = group)
+//     and updates CsvState (c1/c2, norm, stop flag, step counter) in device memory; or
+//   * multi-GPU row slabs (P2P): copies this rank's group sums into every peer's group-sum array over NVLink and
+//     bumps arrive[rank] in every peer's CommBox (st.release.sys after a system fence).  A one-warp kernel
+//     (csv_wait_fold_kernel) between two step launches waits until all ranks have arrived and folds -- the same
+//     numbers in the same order on every rank => bit-identical c1/c2 and stop decision everywhere.
+// Groups are keyed to GLOBAL segment indices, so a slab run over 1/2/4/8 GPUs adds exactly the same numbers in
+// exactly the same order as the single-GPU run.  No floating-point atomics anywhere.
 #pragma once
+#include "comm.cuh"
 #include "common.cuh"
 
 namespace cvb {
@@ -23,28 +29,30 @@ __device__ __forceinline__ bool slot_used(int v) {
     return v <= NCH || v == ACC_SQ || (INIT && v >= ACC_I && v < ACC_I + NCH);
 }
 
+// Whole warp: add the group sums of reduction `prod` of image `img` (lane g holds group g, fixed xor tree) and let
+// lane 0 update the state.  mode 0: after a step; 1: init with reset (stop condition, counters); 2: means only.
 // src/main.cpp:255-281 with H = a + 1/2: c1 = sum I*H / sum H, c2 = sum I*(1-H) / sum (1-H).
-__device__ inline void region_means_from_sums(CsvState *st, const double *tot, int nch, double npix) {
-    const double hs = 0.5 * npix + tot[ACC_A];
-    const double gs = 0.5 * npix - tot[ACC_A];
-    for (int k = 0; k < nch; ++k) {
-        st->c1[k] = (0.5 * st->sumI[k] + tot[ACC_IA + k]) / hs;
-        st->c2[k] = (0.5 * st->sumI[k] - tot[ACC_IA + k]) / gs;
-    }
-}
-
-// One thread per image: add the group sums in index order and update the state.
-// mode 0: after a step; 1: init with reset (stop condition, counters); 2: init without reset (means only)
-__device__ inline void csv_finalize_image(const CsvArgs &A, int img, int mode) {
+__device__ __forceinline__ void csv_fold(const CsvArgs &A, int img, int mode, unsigned int prod) {
     const Geom &G = A.g;
-    CsvState *st = A.state + img;
+    const int lane = threadIdx.x & 31;
+    static_assert(NGROUPS == 32, "one lane per reduction group");
+    const double *gs = A.group_sums + ((size_t)(prod & 1u) * NGROUPS + lane) * G.count * NACC + (size_t)img * NACC;
     double tot[NACC];
-    for (int v = 0; v < NACC; ++v) tot[v] = 0.0;
-    for (int grp = 0; grp < NGROUPS; ++grp)
-        for (int v = 0; v < NACC; ++v) tot[v] += ld_cg(A.group_sums + ((size_t)grp * G.count + img) * NACC + v);
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) tot[v] = ld_cg(gs + v);
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tot[v] += __shfl_xor_sync(0xffffffffu, tot[v], off);
+    }
+    if (lane != 0) return;
+    CsvState *st = A.state + img;
+#pragma unroll
     for (int v = 0; v < NACC; ++v) st->sums[v] = tot[v];
-    if (mode != 0)
-        for (int k = 0; k < G.nch; ++k) st->sumI[k] = tot[ACC_I + k];
+    if (mode != 0) {
+#pragma unroll
+        for (int k = 0; k < MAX_CH; ++k) st->sumI[k] = tot[ACC_I + k];
+    }
     if (mode == 1) {
         st->stop = A.tol * sqrt(tot[ACC_SQ]);  // src/main.cpp:959
         st->norm = __longlong_as_double(0x7ff8000000000000LL);
@@ -56,15 +64,34 @@ __device__ inline void csv_finalize_image(const CsvArgs &A, int img, int mode) {
         st->steps_done += 1;
         st->done = (nrm <= st->stop) ? 1 : 0;  // src/main.cpp:1000
     }
-    region_means_from_sums(st, tot, G.nch, (double)G.h * (double)G.w);
+    const double npix = (double)G.h * (double)G.w;
+    const double hs = 0.5 * npix + tot[ACC_A], gsum = 0.5 * npix - tot[ACC_A];
+#pragma unroll
+    for (int k = 0; k < MAX_CH; ++k) {
+        st->c1[k] = (0.5 * st->sumI[k] + tot[ACC_IA + k]) / hs;
+        st->c2[k] = (0.5 * st->sumI[k] - tot[ACC_IA + k]) / gsum;
+    }
 }
 
-// Called by the whole warp (= the whole CTA) after the row loop.  acc holds per-lane sums.
-// No block-level barrier anywhere: a CTA is one warp, so warps never wait for one another and a finished warp frees
-// its slot at once.  The last warp of a group adds the group's partial vectors in index order.
+// Whole warp (P2P multi-GPU, between two launches): wait until every rank has pushed reduction `produced`, fold it.
+__device__ __forceinline__ void csv_wait_fold(const CsvArgs &A) {
+    CommBox *b = A.cv.box;
+    const int lane = threadIdx.x & 31;
+    const unsigned int prod = ld_relaxed(&b->produced);
+    if (ld_relaxed(&b->finalized) == prod) return;  // nothing new (e.g. the image is frozen: launches were no-ops)
+    if (lane < A.cv.nranks)
+        while (ld_acquire_sys(&b->arrive[lane]) < prod) {
+        }
+    __syncwarp();
+    __threadfence_system();
+    csv_fold(A, 0, b->pending_mode, prod);
+    if (lane == 0) b->finalized = prod;
+}
+
+// Whole warp, after the row loop.  acc holds per-lane sums.
 template <int NCH, bool INIT>
 __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, int cb, int ncb, double (&acc)[NACC],
-                                            int final_mode) {
+                                            int final_mode, bool pushed_rows = false) {
     const Geom &G = A.g;
     const int lane = threadIdx.x & 31;
     CsvState *st = A.state + img;
@@ -81,6 +108,8 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
     const int sb = max(group_seg_begin(grp, G.nseg_global), G.seg0) - G.seg0;
     const int se = min(group_seg_begin(grp + 1, G.nseg_global), G.seg0 + G.nseg) - G.seg0;
     int last = 0;
+    if (pushed_rows) __threadfence_system();  // this warp stored boundary rows into a neighbour's halo
+    __syncwarp();
     if (lane == 0) {
 #pragma unroll
         for (int v = 0; v < NACC; ++v)
@@ -109,21 +138,49 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) sum[v] += __shfl_xor_sync(0xffffffffu, sum[v], off);
         }
+    const bool p2p = A.cv.p2p != 0;
+    // multi-GPU: this reduction's number; its parity picks the group-sum buffer (double buffering against slow peers)
+    const unsigned int prod = p2p ? ld_relaxed(&A.cv.box->produced) + 1u : 0u;
+    double *gbase = A.group_sums + (size_t)(prod & 1u) * NGROUPS * G.count * NACC;
+    int all_done = 0;
     if (lane == 0) {
-        double *gsum = A.group_sums + ((size_t)grp * G.count + img) * NACC;
+        double *gsum = gbase + ((size_t)grp * G.count + img) * NACC;
 #pragma unroll
         for (int v = 0; v < NACC; ++v) gsum[v] = slot_used<NCH, INIT>(v) ? sum[v] : 0.0;
         st->group_ticket[grp] = 0u;
-        if (!A.multi_rank) {
+        if (!A.multi_rank || p2p) {
             __threadfence();
             const unsigned int old = atomicAdd(&st->final_ticket, 1u);
             if (old == (unsigned int)A.ngroups_local - 1u) {
-                __threadfence();
                 st->final_ticket = 0u;
-                csv_finalize_image(A, img, final_mode);
+                all_done = 1;
             }
         }
     }
+    all_done = __shfl_sync(0xffffffffu, all_done, 0);
+    if (!all_done) return;
+    // ---- every local group of this image is summed
+    __threadfence();
+    if (!p2p) {
+        csv_fold(A, img, final_mode, 0u);
+        return;
+    }
+    // slab session (count == 1): this rank's group sums go to every peer, then the arrival flags
+    const size_t first = (size_t)A.group_lo * G.count * NACC;
+    const int nval = (A.group_hi - A.group_lo) * G.count * NACC;
+    for (int p = 0; p < A.cv.nranks; ++p) {
+        if (p == A.cv.rank) continue;
+        double *dst = A.cv.peer_group[p] + (size_t)(prod & 1u) * NGROUPS * G.count * NACC + first;
+        for (int i = lane; i < nval; i += 32) dst[i] = ld_cg(gbase + first + i);
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        A.cv.box->pending_mode = final_mode;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int *>(&A.cv.box->produced) = prod;
+    }
+    if (lane < A.cv.nranks) st_release_sys(&A.cv.peer_box[lane]->arrive[A.cv.rank], prod);
 }
 
 }  // namespace cvb

@@ -419,8 +419,8 @@ def levelset_circ(h, w, cx, cy, radius):
     return u
 
 
-def auto_tile_rows(h, w, count=1):
-    return _ffi.lib().cvb_auto_tile_rows(h, w, count)
+def auto_tile_rows(h, w, count=1, nranks=1):
+    return _ffi.lib().cvb_auto_tile_rows(h, w, count, nranks)
 
 
 def slab_partition(h, tile_rows, nranks, rank):

@@ -105,8 +105,9 @@ cvb_status cvb_levelset_rect(int h, int w, int x, int y, int rw, int rh, double 
 /* InteractiveDataCirc::get_levelset, src/InteractiveDataCirc.cpp:18-25: one-pixel ring of 1 on 0. */
 cvb_status cvb_levelset_circ(int h, int w, int cx, int cy, int radius, double *u);
 
-/* Rows per tile the library would pick for a job of `count` h x w images (what tile_rows = 0 means). */
-int cvb_auto_tile_rows(int h, int w, int count);
+/* Rows per tile the library would pick for a job of `count` h x w images cut into `nranks` row slabs (what
+ * tile_rows = 0 means; nranks = 1 for whole images and batches). */
+int cvb_auto_tile_rows(int h, int w, int count, int nranks);
 /* Row slab [*row_lo, *row_hi) of rank `rank` of `nranks` (1, 2, 4, 8, 16 or 32) for an image of h rows cut
  * into tiles of tile_rows rows: slabs are unions of the library's 32 fixed reduction groups, so a slab run
  * adds the same partial sums in the same order as the single-GPU run (bit-identical results). */
