@@ -289,16 +289,14 @@ extern "C" cvb_status cvb_context_create(int device, void *stream, cvb_context *
         c->own_stream = true;
     }
     for (auto &e : c->ev) cudaEventCreate(&e);
-    // atan(c_q)/pi table of math.cuh, from the host libm
-    double tab[34];
-    tab[0] = 0.0;
-    for (int q = 0; q < 32; ++q) {
+    // atan(c_q)/pi table of math.cuh, from the host libm: quarter-octave centres from 2^-4 up to 2^44
+    double tab[192];
+    for (int q = 0; q < 192; ++q) {
         const uint64_t bits = ((uint64_t)(((1019u * 4u + (unsigned)q) << 18) | 0x00020000u)) << 32;
         double cq;
         memcpy(&cq, &bits, 8);
-        tab[1 + q] = atan(cq) / kPi;
+        tab[q] = atan(cq) / kPi;
     }
-    tab[33] = 0.5;
     if (cudaMalloc(&c->d_atan_tab, sizeof tab) != cudaSuccess ||
         cudaMemcpy(c->d_atan_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) {
         cvb_status st = fail(nullptr, CVB_ERR_CUDA, "context set-up: %s", cudaGetErrorString(cudaGetLastError()));

@@ -94,7 +94,7 @@ struct CsvArgs {
     double *partials;       // [count][nseg][ncb][NACC]
     double *group_sums;     // [2][NGROUPS][count][NACC] (second copy: P2P double buffering)
     double *kappa_out;      // MODE_KAPPA only
-    const double *atan_tab; // 34 entries, see math.cuh
+    const double *atan_tab; // ATAN_NQ entries, see math.cuh
     double alpha, beta, gamma;  // mu*dt, (1/N)*dt, -nu*dt (src/main.cpp:985 as one addWeighted)
     double eps, inv_eps;
     double lambda1[MAX_CH], lambda2[MAX_CH];

@@ -190,15 +190,18 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
         }
         t0 = fma(kap0, K.alphap, t0);
         t1 = fma(kap1, K.alphap, t1);
-        const double du0 = t0 * fast_rcp(fma(C.x, C.x, K.eps2));
-        const double du1 = t1 * fast_rcp(fma(C.y, C.y, K.eps2));
+        // one reciprocal for both pixels: 1/s0 = s1/(s0*s1), 1/s1 = s0/(s0*s1)
+        const double s0 = fma(C.x, C.x, K.eps2), s1 = fma(C.y, C.y, K.eps2);
+        const double rs = fast_rcp(s0 * s1);
+        const double du0 = t0 * (rs * s1);
+        const double du1 = t1 * (rs * s0);
         const double un0 = C.x + du0, un1 = C.y + du1;
         if (lane) *reinterpret_cast<double2 *>(po) = make_double2(un0, un1);
         po += pitch;
 
         // sums of the updated level set and of du^2 (lane 0 is a halo lane: its sums are dropped at the end)
-        const double a0 = atan_over_pi(un0 * K.inv_eps, s_tab);
-        const double a1 = atan_over_pi(un1 * K.inv_eps, s_tab);
+        double a0, a1;
+        atan_over_pi2(un0 * K.inv_eps, un1 * K.inv_eps, s_tab, a0, a1);
         accA += a0;
         accA += a1;
 #pragma unroll
@@ -227,7 +230,7 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
 template <int NCH, bool STRICT, int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(const __grid_constant__ CsvArgs A) {
     const Geom &G = A.g;
-    __shared__ double s_tab[ATAN_TAB_N + 2];
+    __shared__ double s_tab[ATAN_TAB_N];
     const int lane = threadIdx.x;
     constexpr int warp = 0;
     int bid = blockIdx.x;
@@ -236,8 +239,8 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     const int seg = bid % G.nseg;
     const int img = bid / G.nseg;
     CsvState *st = A.state + img;
-    s_tab[lane] = A.atan_tab[lane];
-    if (lane < ATAN_TAB_N - 32) s_tab[32 + lane] = A.atan_tab[32 + lane];
+#pragma unroll
+    for (int q = 0; q < ATAN_TAB_N; q += 32) s_tab[q + lane] = A.atan_tab[q + lane];
     const int2 ds = *reinterpret_cast<const int2 *>(&st->done);  // {done, steps_done}
     if (MODE == MODE_STEP && ds.x) return;  // frozen image: the launch is a no-op (src/main.cpp:1000)
     __syncwarp();
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
 template <int NCH>
 __global__ void __launch_bounds__(CTA_THREADS, 8) csv_init_kernel(const __grid_constant__ CsvArgs A, int final_mode) {
     const Geom &G = A.g;
-    __shared__ double s_tab[ATAN_TAB_N + 2];
+    __shared__ double s_tab[ATAN_TAB_N];
     const int lane = threadIdx.x;
     constexpr int warp = 0;
     int bid = blockIdx.x;
@@ -492,8 +495,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) csv_init_kernel(const __grid_c
     const int seg = bid % G.nseg;
     const int img = bid / G.nseg;
     CsvState *st = A.state + img;
-    s_tab[lane] = A.atan_tab[lane];
-    if (lane < ATAN_TAB_N - 32) s_tab[32 + lane] = A.atan_tab[32 + lane];
+#pragma unroll
+    for (int q = 0; q < ATAN_TAB_N; q += 32) s_tab[q + lane] = A.atan_tab[q + lane];
     __syncwarp();
     const int par = (final_mode == 1) ? 0 : (st->steps_done & 1);
     const double *__restrict__ uin = A.u[par] + (size_t)img * G.plane_elems;

@@ -4,8 +4,8 @@
 // traffic is down to 16+N bytes/pixel, so the production ("fast") math counts FP64 instructions:
 //   * reciprocal / rsqrt = MUFU seed (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64) + ONE cubic
 //     Newton step (3 resp. 5 DFMA-class ops, ~1 ulp), no IEEE division or sqrt sequences;
-//   * atan(x)/pi by a 32-interval table-driven argument reduction with one reciprocal and a degree-5
-//     polynomial (17 FP64 ops, <= 4 ulp; the CUDA libm atan is ~2x that);
+//   * atan(x)/pi by a 192-interval table-driven argument reduction with one reciprocal and a degree-5
+//     polynomial (17 FP64 ops, <= 4 ulp, branch-free; the CUDA libm atan is ~2x that);
 //   * uint8 -> double through the 2^52 magic constant (1 DADD instead of a quarter-rate I2F.F64).
 // "Strict" math reproduces the oracle's operation order with IEEE div/sqrt and no FMA contraction
 // (the reference build has no FMA and forbids reassociation, Makefile:16): a test mode.
@@ -53,26 +53,27 @@ __device__ __forceinline__ double u8_to_double(unsigned int v) {
 }
 
 // ---- atan(x)/pi ------------------------------------------------------------------------------------
-// t = |x|.  t < 2^4: c = centre of the quarter-octave of max(t, 2^-4) (exponent and top two mantissa bits kept,
-// third bit set); atan t = atan c + atan z, z = (t-c)/(1+t*c), |z| <= 0.0704.  t >= 2^4: atan t = pi/2 +
-// atan(-1/t).  tab[1+q] = atan(c_q)/pi (q = 0..31), tab[33] = 1/2 (tab[0] unused).
-constexpr int ATAN_TAB_N = 34;
-constexpr int ATAN_Q0 = 1019 * 4;  // (biased exponent of 2^-4) * 4
+// t = |x| clamped to [2^-4, 2^44): c = centre of t's quarter-octave (exponent and top two mantissa bits kept, third
+// bit set); atan t = atan c + atan z with z = (t-c)/(1+t*c), |z| <= 0.0704 (for t < 2^-4 the first centre is
+// shared: the ABSOLUTE error stays ~1e-17, which is what the sums of a = H - 1/2 need; for t >= 2^44 the last centre
+// is shared: z < 6e-14).  No branches, no selects: tab[q] = atan(c_q)/pi, q = 0..191, lives in shared memory.
+constexpr int ATAN_NQ = 192;
+constexpr int ATAN_TAB_N = ATAN_NQ;
+constexpr int ATAN_Q0 = 1019 * 4;                        // (biased exponent of 2^-4) * 4
+constexpr int ATAN_HC_MIN = 0x3fb00000;                  // hi word of 2^-4
+constexpr int ATAN_HC_MAX = ((1023 + 43) << 20) | 0xfffff;  // hi word just below 2^44
 
-__device__ __forceinline__ double atan_over_pi(double x, const double *tab /* shared memory */) {
-    const int hx = __double2hiint(x);
+__device__ __forceinline__ void atan_reduce(double x, const double *tab, int &hx, double &num, double &den, double &hi) {
+    hx = __double2hiint(x);
     const int ht = hx & 0x7fffffff;
     const double t = __hiloint2double(ht, __double2loint(x));
-    // t < 2^-4 shares the first interval's centre: |z| <= 0.0704 and the ABSOLUTE error stays ~1e-17, which is
-    // what the sums of a = H - 1/2 need (no separate small-argument branch)
-    const int hc = max(ht, 0x3fb00000);
-    const int q1 = (hc >> 18) - (ATAN_Q0 - 1);  // >= 1
-    const bool big = q1 > 32;
+    const int hc = min(max(ht, ATAN_HC_MIN), ATAN_HC_MAX);
     const double c = __hiloint2double((hc & 0xfffc0000) | 0x00020000, 0);
-    const double hi = tab[min(q1, 33)];
-    const double num = big ? -1.0 : t - c;
-    const double den = big ? t : fma(t, c, 1.0);
-    const double z = num * fast_rcp(den);
+    hi = tab[(hc >> 18) - ATAN_Q0];
+    num = t - c;
+    den = fma(t, c, 1.0);
+}
+__device__ __forceinline__ double atan_finish(double z, double hi, int hx) {
     const double w = z * z;
     double p = fma(w, 1.0 / 13.0, -1.0 / 11.0);
     p = fma(p, w, 1.0 / 9.0);
@@ -83,6 +84,22 @@ __device__ __forceinline__ double atan_over_pi(double x, const double *tab /* sh
     const double at = fma(zw, p, z);           // atan z
     const double r = fma(at, CVB_INV_PI, hi);  // atan(t)/pi
     return __hiloint2double(__double2hiint(r) ^ (hx & 0x80000000), __double2loint(r));
+}
+__device__ __forceinline__ double atan_over_pi(double x, const double *tab /* shared memory */) {
+    int hx;
+    double num, den, hi;
+    atan_reduce(x, tab, hx, num, den, hi);
+    return atan_finish(num * fast_rcp(den), hi, hx);
+}
+// two arguments sharing ONE reciprocal: 1/d0 = d1/(d0*d1), 1/d1 = d0/(d0*d1)  (d in [1, 2^90): no overflow)
+__device__ __forceinline__ void atan_over_pi2(double x0, double x1, const double *tab, double &a0, double &a1) {
+    int hx0, hx1;
+    double n0, d0, h0, n1, d1, h1;
+    atan_reduce(x0, tab, hx0, n0, d0, h0);
+    atan_reduce(x1, tab, hx1, n1, d1, h1);
+    const double r = fast_rcp(d0 * d1);
+    a0 = atan_finish(n0 * (r * d1), h0, hx0);
+    a1 = atan_finish(n1 * (r * d0), h1, hx1);
 }
 
 // ---- curvature normal component n = up / sqrt(up^2 + uc^2 + eta^2), src/main.cpp:365-368 --------------
