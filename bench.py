@@ -32,6 +32,9 @@ PM = dict(K=10.0, L=0.25, T=5.0)   # 20 diffusion steps
 CSV_STEPS = 100
 BYTES_CSV_RGB = 19.0               # read u 8 + write u 8 + 3 x uint8
 BYTES_PM_RGB = 48.0                # (read 8 + write 8) x 3 channels
+# dram__bytes_read.sum + dram__bytes_write.sum of csv_step_kernel<3> from the ncu --set full capture
+# profiles/r1c_ncu_full_csv_step.csv (8192^2 RGB: 1.262 GB per launch vs 1.275 GB algorithmic)
+NCU_TRAFFIC_RATIO_CSV = 1.262 / 1.275
 
 
 def measured_peak():
@@ -134,7 +137,8 @@ def workload_config(args, world):
     return {"workload": "configs[3]: synthetic %dx%d RGB PM+CSV (PM -K 10 -L 0.25 -T 5 = 20 steps, CSV -N %d -t 0, "
                         "checkerboard init)%s" % (s, s, CSV_STEPS, "" if s == 16384 else " [REDUCED SIZE]"),
             "h": s, "w": s, "channels": 3, "pm_steps": 20, "csv_steps": CSV_STEPS,
-            "decomposition": "row slabs x%d, NCCL halo + region-sum all-gather per step" % world if world > 1 else "single GPU",
+            "decomposition": ("row slabs x%d, boundary rows + region sums pushed into peer memory (CUDA IPC over NVLink), "
+                              "flag-synchronised; CVB_COMM=nccl switches to NCCL send/recv + all-gather" % world) if world > 1 else "single GPU",
             "l2": "inputs larger than L2 (u ping-pong %.1f GB per GPU)" % (2 * 8.0 * s * s / world / 1e9)}
 
 
@@ -247,7 +251,8 @@ def run_b200(args):
                 "h2d_bytes_per_step": st_e2e["h2d_bytes"] // args.steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] // args.steps},
         "gpu_launches": int(st["kernel_launches"]),
         "roofline": {"bound": "hbm", "kernel": "csv_step_kernel<3,fast>", "achieved": csv_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": csv_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": csv_gbs / peak, "traffic": NCU_TRAFFIC_RATIO_CSV * BYTES_CSV_RGB * rows * w,
+                     "traffic_source": "profiles/r1c_ncu_full_csv_step.csv (ncu at 8192^2, scaled by pixels)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_CSV_RGB * rows * w, "launch_ms": csv_launch_ms,
                      "share_of_step": st["csv_ms"] / ms},
         "kernels": {"csv_step": {"launches": int(st["csv_step_launches"]), "ms_per_launch": csv_launch_ms, "GBps": csv_gbs,
