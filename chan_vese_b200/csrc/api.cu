@@ -573,6 +573,8 @@ static cvb_status job_upload_image(Job *j, const uint8_t *const *planes) {
                                 rows, cudaMemcpyHostToDevice, c->stream));
         c->stats.h2d_bytes += (uint64_t)rows * g.w;
     }
+    CU(c, launch_replicate_halo(j->d_img, (size_t)g.plane_elems, (size_t)g.pitch, g.count * g.nch, rows, g.row_lo == 0,
+                                g.row_hi == g.h, c->stream));
     TRY(exchange_halo(j, j->d_img, 1, g.count * g.nch));
     CU(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffers on return
     return CVB_OK;
@@ -629,6 +631,8 @@ static cvb_status job_upload_levelset(Job *j, int index, const double *u) {
                                   (size_t)rows * g.pitch * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         }
     }
+    CU(c, launch_replicate_halo(j->d_u[0] + (size_t)lo * g.plane_elems, (size_t)g.plane_elems * sizeof(double),
+                                (size_t)g.pitch * sizeof(double), hi - lo, rows, g.row_lo == 0, g.row_hi == g.h, c->stream));
     CU(c, cudaMemsetAsync(j->d_state + lo, 0, (size_t)(hi - lo) * sizeof(CsvState), c->stream));
     CU(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffer on return
     return CVB_OK;
@@ -688,6 +692,8 @@ static cvb_status job_init_checkerboard(Job *j) {
                                   g.row_hi - g.row_lo, g.w, g.pitch, c->stream));
         c->stats.kernel_launches += 1;
     }
+    CU(c, launch_replicate_halo(j->d_u[0], (size_t)g.plane_elems * sizeof(double), (size_t)g.pitch * sizeof(double), g.count,
+                                g.row_hi - g.row_lo, g.row_lo == 0, g.row_hi == g.h, c->stream));
     CU(c, cudaMemsetAsync(j->d_state, 0, (size_t)g.count * sizeof(CsvState), c->stream));
     CU(c, cudaStreamSynchronize(c->stream));  // s goes out of scope
     return CVB_OK;

@@ -72,6 +72,22 @@ __device__ __noinline__ bool push_boundary_rows(const CsvArgs &A, const double *
     return pushed;
 }
 
+// BORDER_REPLICATE in i for the fast path: the halo rows above row 0 and below row h-1 of the buffer just written
+// get copies of those rows (each lane copies the two columns it owns; read back from L2, outside the hot loop).
+__device__ __noinline__ void replicate_border_rows(double *uout, const Geom &G, int ra, int rb, int a) {
+    if (ra == 0) {
+        const double2 v = __ldcg(reinterpret_cast<const double2 *>(uout + (size_t)(0 - G.row_lo + HALO) * G.pitch + a));
+        *reinterpret_cast<double2 *>(uout + (size_t)0 * G.pitch + a) = v;
+        *reinterpret_cast<double2 *>(uout + (size_t)1 * G.pitch + a) = v;
+    }
+    if (rb == G.h) {
+        const size_t last = (size_t)(G.h - 1 - G.row_lo + HALO);
+        const double2 v = __ldcg(reinterpret_cast<const double2 *>(uout + last * G.pitch + a));
+        *reinterpret_cast<double2 *>(uout + (last + 1) * G.pitch + a) = v;
+        *reinterpret_cast<double2 *>(uout + (last + 2) * G.pitch + a) = v;
+    }
+}
+
 // Coefficients of one step, derived from the region means once per thread.
 template <int NCH>
 struct StepCoef {
@@ -79,6 +95,7 @@ struct StepCoef {
     double q0;                // constant part: gamma' + sum_k C_k
     double alphap;            // mu*dt * eps/pi
     double eps2, inv_eps;
+    bool linear;              // all A_k == 0 (lambda1 == lambda2, the reference's default): the data term is linear in I
 };
 
 // ---- interior fast path ---------------------------------------------------------------------------------
@@ -86,21 +103,30 @@ struct StepCoef {
 // no border selects, no validity masks; the row recurrence carries u(i) - u(i-1) instead of row i-1, so
 // only two row ages are live and a 2x unrolled loop needs no register moves.  One output row per iteration:
 //   in:  C = u(i,.), dN = u(i,.) - u(i-1,.), nyp = ny(i-1,.), S = u(i+1,.)
-template <int NCH>
+// EDGE: the strip touches the left or right image border (BORDER_REPLICATE in j, :351,353, and on the normalised
+// field, :371): loads are predicated, the first column has no west neighbour and a zero x-term, the last column no
+// east neighbour, columns beyond w are neither stored nor summed.  Interior strips compile all of that away.
+template <int NCH, bool EDGE>
 __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, double *__restrict__ uout,
                                               const uint8_t *__restrict__ im, const Geom &G, const StepCoef<NCH> &K,
                                               const double *s_tab, int ra, int rb, int a, int lane, double (&acc)[NACC]) {
+    const int w = G.w;
+    const bool colok = !EDGE || (a >= 0 && a < G.pitch);
+    const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
+    const bool v0 = lane >= 1 && (!EDGE || a < w), v1 = lane >= 1 && (!EDGE || a + 1 < w);
+    auto ld2 = [&](const double *p) { return colok ? __ldg(reinterpret_cast<const double2 *>(p)) : make_double2(0.0, 0.0); };
+    auto ldi = [&](const uint8_t *p) -> unsigned int { return colok ? __ldg(reinterpret_cast<const unsigned short *>(p)) : 0u; };
     const size_t pitch = (size_t)G.pitch;
     const double *pu = uin + (size_t)(ra - 2 - G.row_lo + HALO) * pitch + a;  // row ra-2
     double *po = uout + (size_t)(ra - G.row_lo + HALO) * pitch + a;           // row ra
     const uint8_t *pi = im + (size_t)(ra - G.row_lo + HALO) * pitch + a;      // row ra, channel 0
     const size_t pe = (size_t)G.plane_elems;
-    const bool l31 = lane == 31;
+    const bool l31 = lane == 31 && (!EDGE || a + 2 < G.pitch);
 
     // prime: rows ra-2, ra-1, ra
-    const double2 R0 = __ldg(reinterpret_cast<const double2 *>(pu));
-    const double2 R1 = __ldg(reinterpret_cast<const double2 *>(pu + pitch));
-    double2 C = __ldg(reinterpret_cast<const double2 *>(pu + 2 * pitch));
+    const double2 R0 = ld2(pu);
+    const double2 R1 = ld2(pu + pitch);
+    double2 C = ld2(pu + 2 * pitch);
     double e2c = l31 ? __ldg(pu + 2 * pitch + 2) : 0.0;
     double dN0 = C.x - R1.x, dN1 = C.y - R1.y;
     double nyp0 = normal_component<false>(dN0, dN0 + (R1.x - R0.x));
@@ -108,20 +134,26 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
     pu += 3 * pitch;  // row ra+1
 
     // register prefetch: rows i+1 and i+2 of u, rows i and i+1 of the image
-    double2 q0 = __ldg(reinterpret_cast<const double2 *>(pu)), q1 = make_double2(0.0, 0.0);
+    double2 q0 = ld2(pu), q1 = make_double2(0.0, 0.0);
+    if (ra == 0) {
+        // image top: the halo rows hold copies of row 0 (BORDER_REPLICATE), so dN = 0; the y-term of kappa must vanish
+        // in row 0 (ny(-1) := ny(0), src/main.cpp:372): start from the very value the loop will compute for ny(0)
+        nyp0 = normal_component<false>(q0.x - C.x, (q0.x - C.x) + dN0);
+        nyp1 = normal_component<false>(q0.y - C.y, (q0.y - C.y) + dN1);
+    }
     double f0 = l31 ? __ldg(pu + 2) : 0.0, f1 = 0.0;
     unsigned int j0[NCH], j1[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        j0[c] = __ldg(reinterpret_cast<const unsigned short *>(pi + c * pe));
+        j0[c] = ldi(pi + c * pe);
         j1[c] = 0u;
     }
     const int n = rb - ra;
     if (n > 1) {
-        q1 = __ldg(reinterpret_cast<const double2 *>(pu + pitch));
+        q1 = ld2(pu + pitch);
         if (l31) f1 = __ldg(pu + pitch + 2);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) j1[c] = __ldg(reinterpret_cast<const unsigned short *>(pi + pitch + c * pe));
+        for (int c = 0; c < NCH; ++c) j1[c] = ldi(pi + pitch + c * pe);
     }
     pu += 2 * pitch;  // row ra+3: next row to fetch
     pi += 2 * pitch;  // row ra+2
@@ -139,10 +171,10 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
         for (int c = 0; c < NCH; ++c) Ib[c] = j0[c];
 #ifdef CSV_FAST_D1
         if (r + 1 < n) {  // one row ahead only: rows (ra+r)+2 of u and (ra+r)+1 of the image
-            q0 = __ldg(reinterpret_cast<const double2 *>(pu - pitch));
+            q0 = ld2(pu - pitch);
             if (l31) f0 = __ldg(pu - pitch + 2);
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) j0[c] = __ldg(reinterpret_cast<const unsigned short *>(pi - pitch + c * pe));
+            for (int c = 0; c < NCH; ++c) j0[c] = ldi(pi - pitch + c * pe);
         }
 #else
         q0 = q1;
@@ -150,10 +182,10 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
 #pragma unroll
         for (int c = 0; c < NCH; ++c) j0[c] = j1[c];
         if (r + 2 < n) {  // rows (ra+r)+3 of u and (ra+r)+2 of the image
-            q1 = __ldg(reinterpret_cast<const double2 *>(pu));
+            q1 = ld2(pu);
             if (l31) f1 = __ldg(pu + 2);
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) j1[c] = __ldg(reinterpret_cast<const unsigned short *>(pi + c * pe));
+            for (int c = 0; c < NCH; ++c) j1[c] = ldi(pi + c * pe);
         }
 #endif
         if (CSV_PF > 0 && r + CSV_PF < n) {
@@ -167,13 +199,21 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
         const double upy0 = S.x - C.x, upy1 = S.y - C.y;
         const double ny0 = normal_component<false>(upy0, upy0 + dN0);
         const double ny1 = normal_component<false>(upy1, upy1 + dN1);
-        const double Wn = __shfl_up_sync(0xffffffffu, C.y, 1);
+        double Wn = __shfl_up_sync(0xffffffffu, C.y, 1);
         double E2 = __shfl_down_sync(0xffffffffu, C.x, 1);
-        E2 = l31 ? e2c : E2;
-        const double nx0 = normal_component<false>(C.y - C.x, C.y - Wn);
+        E2 = (lane == 31) ? e2c : E2;
+        double E0 = C.y;
+        if (EDGE) {
+            Wn = first ? C.x : Wn;
+            E0 = last0 ? C.x : C.y;
+            E2 = last1 ? C.y : E2;
+        }
+        const double nx0 = normal_component<false>(E0 - C.x, E0 - Wn);
         const double nx1 = normal_component<false>(E2 - C.y, E2 - C.x);
         const double nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
-        const double kap0 = (nx0 - nxw) + (ny0 - nyp0);
+        double kx0 = nx0 - nxw;
+        if (EDGE) kx0 = first ? 0.0 : kx0;
+        const double kap0 = kx0 + (ny0 - nyp0);
         const double kap1 = (nx1 - nx0) + (ny1 - nyp1);
         // data term + combine (:968-985), delta (:988-992), update (:994)
         double I0[NCH], I1[NCH];
@@ -183,10 +223,18 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
             I1[c] = u8_to_double(Ib[c] >> 8);
         }
         double t0 = K.q0, t1 = K.q0;
+        if (K.linear) {  // warp-uniform
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            t0 = fma(fma(K.cA[c], I0[c], K.cB[c]), I0[c], t0);
-            t1 = fma(fma(K.cA[c], I1[c], K.cB[c]), I1[c], t1);
+            for (int c = 0; c < NCH; ++c) {
+                t0 = fma(K.cB[c], I0[c], t0);
+                t1 = fma(K.cB[c], I1[c], t1);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                t0 = fma(fma(K.cA[c], I0[c], K.cB[c]), I0[c], t0);
+                t1 = fma(fma(K.cA[c], I1[c], K.cB[c]), I1[c], t1);
+            }
         }
         t0 = fma(kap0, K.alphap, t0);
         t1 = fma(kap1, K.alphap, t1);
@@ -196,12 +244,26 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
         const double du0 = t0 * (rs * s1);
         const double du1 = t1 * (rs * s0);
         const double un0 = C.x + du0, un1 = C.y + du1;
-        if (lane) *reinterpret_cast<double2 *>(po) = make_double2(un0, un1);
+        if (EDGE) {
+            if (v1)
+                *reinterpret_cast<double2 *>(po) = make_double2(un0, un1);
+            else if (v0)
+                *po = un0;
+        } else if (lane) {
+            *reinterpret_cast<double2 *>(po) = make_double2(un0, un1);
+        }
         po += pitch;
 
         // sums of the updated level set and of du^2 (lane 0 is a halo lane: its sums are dropped at the end)
         double a0, a1;
         atan_over_pi2(un0 * K.inv_eps, un1 * K.inv_eps, s_tab, a0, a1);
+        double dq0 = du0, dq1 = du1;
+        if (EDGE) {  // columns beyond the image do not count
+            a0 = v0 ? a0 : 0.0;
+            a1 = v1 ? a1 : 0.0;
+            dq0 = v0 ? du0 : 0.0;
+            dq1 = v1 ? du1 : 0.0;
+        }
         accA += a0;
         accA += a1;
 #pragma unroll
@@ -209,8 +271,8 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
             accI[c] = fma(I0[c], a0, accI[c]);
             accI[c] = fma(I1[c], a1, accI[c]);
         }
-        accS = fma(du0, du0, accS);
-        accS = fma(du1, du1, accS);
+        accS = fma(dq0, dq0, accS);
+        accS = fma(dq1, dq1, accS);
         // next row
         dN0 = upy0;
         dN1 = upy1;
@@ -268,6 +330,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     K.alphap = 0.0;
     K.eps2 = eps * eps;
     K.inv_eps = inv_eps;
+    K.linear = true;
     double c1[NCH], c2[NCH];
     if (MODE == MODE_STEP) {
         const double kd = eps * CVB_INV_PI;
@@ -280,6 +343,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
             c2[k] = st->c2[k];
             const double l1 = A.lambda1[k], l2 = A.lambda2[k];
             K.cA[k] = bk * (l2 - l1);
+            K.linear = K.linear && (l1 == l2);
             K.cB[k] = 2.0 * bk * (l1 * c1[k] - l2 * c2[k]);
             K.q0 += bk * (l2 * c2[k] * c2[k] - l1 * c1[k] * c1[k]);
         }
@@ -305,9 +369,13 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
 
     // CTAs whose stencils stay inside the image take the fast path (all but the outermost ring)
-    const bool interior = !STRICT && MODE == MODE_STEP && cb > 0 && (cb + 1) * CSV_CB < w && ra >= 2 && rb < h;
+    // (image top and bottom included: the halo rows there hold copies of the border rows, see replicate_border_rows)
+    const bool interior = !STRICT && MODE == MODE_STEP && cb > 0 && (cb + 1) * CSV_CB < w;
+    const bool edge_fast = !STRICT && MODE == MODE_STEP && !interior && cs < w;
     if (interior) {
-        csv_rows_fast<NCH>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
+        csv_rows_fast<NCH, false>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
+    } else if (edge_fast) {
+        csv_rows_fast<NCH, true>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
     } else if (cs < w) {
         const int nk = rb - ra + 3;  // streamed rows ra-2 .. rb
         double2 pq[CSV_D];
@@ -473,6 +541,8 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
         }
     }
     if (MODE == MODE_STEP) {
+        // image top / bottom: keep copies of the border rows in the halo rows of the buffer just written
+        if (cs < w && colok && lane >= 1 && (ra == 0 || rb == h)) replicate_border_rows(uout, G, ra, rb, a);
         // P2P multi-GPU: the slab's first / last HALO rows are the neighbours' halo rows
         bool pushed = false;
         if (A.cv.p2p && cs < w && colok && (ra < G.row_lo + HALO || rb > G.row_hi - HALO))
@@ -585,6 +655,31 @@ __global__ void checkerboard_kernel(double *u, const signed char *si, const sign
     const int i = blockIdx.y;
     if (j >= w || i >= rows) return;
     u[(size_t)(i + HALO) * pitch + j] = (double)((int)si[row_lo + i] * (int)sj[j]);
+}
+
+// Fill the border halo rows of freshly written planes (upload, initialisers): rows -2,-1 := row 0 when the job owns
+// the image top, rows h, h+1 := row h-1 when it owns the bottom.  One thread per 16 bytes of a row.
+__global__ void replicate_halo_kernel(uint8_t *base, size_t plane_bytes, size_t row_bytes, int rows, int top, int bottom) {
+    uint8_t *pl = base + (size_t)blockIdx.y * plane_bytes;
+    const size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x >= row_bytes) return;
+    if (top) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(pl + (size_t)HALO * row_bytes + x);
+        *reinterpret_cast<uint4 *>(pl + x) = v;
+        *reinterpret_cast<uint4 *>(pl + row_bytes + x) = v;
+    }
+    if (bottom) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(pl + (size_t)(HALO + rows - 1) * row_bytes + x);
+        *reinterpret_cast<uint4 *>(pl + (size_t)(HALO + rows) * row_bytes + x) = v;
+        *reinterpret_cast<uint4 *>(pl + (size_t)(HALO + rows + 1) * row_bytes + x) = v;
+    }
+}
+cudaError_t launch_replicate_halo(void *base, size_t plane_bytes, size_t row_bytes, int nplanes, int rows, int top, int bottom,
+                                  cudaStream_t s) {
+    if ((!top && !bottom) || nplanes <= 0) return cudaSuccess;
+    dim3 grid((unsigned int)((row_bytes / 16 + 127) / 128), nplanes);
+    replicate_halo_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<uint8_t *>(base), plane_bytes, row_bytes, rows, top, bottom);
+    return cudaGetLastError();
 }
 
 // ---- host launchers -----------------------------------------------------------------------------------

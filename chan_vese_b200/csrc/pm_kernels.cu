@@ -94,9 +94,22 @@ __device__ __forceinline__ double pm_update(double I0, double IS, double IE, dou
 // reference's; only the order of the final additions differs), so every flux is computed once: the south flux is
 // carried to the next row and the west flux comes from the neighbouring lane.  All row queues are two deep, so a
 // 2x unrolled loop needs no register moves.  Per iteration: row i+2 arrives, g(i+1) is finished, row i is written.
-template <typename TIN, typename TOUT>
+// EDGE: the strip touches the left or right image border: loads are predicated, g = 1 in the border columns (:516),
+// the fluxes across the border are zero (clamped neighbours, :529-530), columns beyond w are not stored.
+template <typename TIN, typename TOUT, bool EDGE>
 __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *__restrict__ out, const Geom &G, int ra,
                                              int rb, int a, int lane, double inv_k2, double lq) {
+    const int w = G.w;
+    const bool colok = !EDGE || (a >= 0 && a < G.pitch);
+    const bool bc0 = EDGE && (a == 0 || a == w - 1), bc1 = EDGE && a + 1 == w - 1;  // border columns
+    const bool nofxw = EDGE && a == 0, nofx0 = EDGE && a == w - 1;
+    auto ldr = [&](const TIN *p) { return colok ? pm_load2<TIN>(p) : make_double2(0.0, 0.0); };
+    auto fixg = [&](double2 &g) {
+        if (EDGE) {
+            g.x = bc0 ? 1.0 : g.x;
+            g.y = bc1 ? 1.0 : g.y;
+        }
+    };
     const size_t pitch = (size_t)G.pitch;
     const TIN *pin = in + (size_t)(ra - 2 - G.row_lo + HALO) * pitch + a;  // row ra-2
     TOUT *po = out + (size_t)(ra - G.row_lo + HALO) * pitch + a;           // row ra
@@ -113,8 +126,8 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
     auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, gy * gy), inv_k2, 1.0)); };  // :518-521
 
     // prologue: rows ra-2 .. ra+1 give g(ra-1), g(ra) and the flux Fy(ra-1/2)
-    const double2 X0 = pm_load2<TIN>(pin), X1 = pm_load2<TIN>(pin + pitch), X2 = pm_load2<TIN>(pin + 2 * pitch),
-                  X3 = pm_load2<TIN>(pin + 3 * pitch);
+    const double2 X0 = ldr(pin), X1 = ldr(pin + pitch), X2 = ldr(pin + 2 * pitch),
+                  X3 = ldr(pin + 3 * pitch);
     double2 rd0, rs0, rd1, rs1, rd2, rs2, rd3, rs3;
     sobel_rows(X0, rd0, rs0);
     sobel_rows(X1, rd1, rs1);
@@ -125,20 +138,23 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
     gP.y = edge((rd0.y + 2.0 * rd1.y) + rd2.y, rs2.y - rs0.y);
     gC.x = edge((rd1.x + 2.0 * rd2.x) + rd3.x, rs3.x - rs1.x);
     gC.y = edge((rd1.y + 2.0 * rd2.y) + rd3.y, rs3.y - rs1.y);
-    double fy0 = (gP.x + gC.x) * (X2.x - X1.x), fy1 = (gP.y + gC.y) * (X2.y - X1.y);  // Fy(ra-1/2)
+    if (ra == 0 || ra == G.h - 1) gC = make_double2(1.0, 1.0);  // g = 1 on the image border rows (:516)
+    fixg(gP);
+    fixg(gC);
+    double fy0 = (gP.x + gC.x) * (X2.x - X1.x), fy1 = (gP.y + gC.y) * (X2.y - X1.y);  // Fy(ra-1/2); 0 at the image top
     double2 IC = X2, IS = X3;                                                  // rows i, i+1
     double2 P = make_double2(fma(2.0, rd3.x, rd2.x), fma(2.0, rd3.y, rd2.y));  // rd(i) + 2 rd(i+1)
     double2 rdB = rd3;                                                         // rd(i+1)
     double2 rsA = rs2, rsB = rs3;                                              // rs(i), rs(i+1)
     pin += 4 * pitch;                                                          // row ra+2
-    double2 q0 = pm_load2<TIN>(pin), q1 = make_double2(0.0, 0.0);
-    if (n > 1) q1 = pm_load2<TIN>(pin + pitch);
+    double2 q0 = ldr(pin), q1 = make_double2(0.0, 0.0);
+    if (n > 1) q1 = ldr(pin + pitch);
     pin += 2 * pitch;  // row ra+4: next row to fetch
 #pragma unroll 2
     for (int r = 0; r < n; ++r) {
         const double2 X = q0;  // row i+2
         q0 = q1;
-        if (r + 2 < n) q1 = pm_load2<TIN>(pin);
+        if (r + 2 < n) q1 = ldr(pin);
         if (PM_PF > 0 && r + PM_PF < n) prefetch_l2(pin + (size_t)(PM_PF - 2) * pitch);
         pin += pitch;
         // g(i+1) from the Sobel sums of rows i, i+1, i+2 (:503-504, :513-522)
@@ -147,16 +163,28 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
         double2 gS;
         gS.x = edge(P.x + rdC.x, rsC.x - rsA.x);
         gS.y = edge(P.y + rdC.y, rsC.y - rsA.y);
-        // fluxes of row i and the update (:524-548)
+        if (ra + r + 1 == G.h - 1) gS = make_double2(1.0, 1.0);  // g = 1 on the last image row (:516)
+        fixg(gS);
+        // fluxes of row i and the update (:524-548); at the image top/bottom the halo rows hold copies of the border
+        // rows (clamped neighbours, :527-528), so the fluxes across the border are exactly zero
         const double fs0 = (gC.x + gS.x) * (IS.x - IC.x), fs1 = (gC.y + gS.y) * (IS.y - IC.y);  // Fy(i+1/2)
         const double Ie = __shfl_down_sync(0xffffffffu, IC.x, 1);
         const double ge = __shfl_down_sync(0xffffffffu, gC.x, 1);
-        const double fx0 = (gC.x + gC.y) * (IC.y - IC.x);        // Fx(a+1/2)
-        const double fx1 = (gC.y + ge) * (Ie - IC.y);            // Fx(a+3/2)
-        const double fxw = __shfl_up_sync(0xffffffffu, fx1, 1);  // Fx(a-1/2)
+        double fx0 = (gC.x + gC.y) * (IC.y - IC.x);        // Fx(a+1/2)
+        double fx1 = (gC.y + ge) * (Ie - IC.y);            // Fx(a+3/2)
+        if (EDGE) {
+            fx0 = nofx0 ? 0.0 : fx0;
+            fx1 = bc1 ? 0.0 : fx1;
+        }
+        double fxw = __shfl_up_sync(0xffffffffu, fx1, 1);  // Fx(a-1/2)
+        if (EDGE) fxw = nofxw ? 0.0 : fxw;
         const double o0 = fma((fs0 - fy0) + (fx0 - fxw), lq, IC.x);
         const double o1 = fma((fs1 - fy1) + (fx1 - fx0), lq, IC.y);
-        if (lane >= 1 && lane <= 30) pm_store(po, o0, o1, true);
+        if (EDGE) {
+            if (lane >= 1 && lane <= 30 && a < w) pm_store(po, o0, o1, a + 1 < w);
+        } else if (lane >= 1 && lane <= 30) {
+            pm_store(po, o0, o1, true);
+        }
         po += pitch;
         // next row
         fy0 = fs0;
@@ -256,6 +284,30 @@ __device__ __forceinline__ void pm_rows_generic(const TIN *__restrict__ in, TOUT
     }
 }
 
+// Clamped neighbours in i for the fast path: the halo rows above row 0 / below row h-1 of the plane just written get
+// copies of those rows (each lane copies the columns it owns, read back from L2).
+template <typename TOUT>
+__device__ __noinline__ void pm_replicate_border(TOUT *out, const Geom &G, int ra, int rb, int a) {
+    const bool two = a + 1 < G.w;
+    if (ra == 0) {
+        const TOUT *src = out + (size_t)(0 - G.row_lo + HALO) * G.pitch + a;
+        const TOUT v0 = __ldcg(src), v1 = two ? __ldcg(src + 1) : v0;
+        for (int k = 0; k < HALO; ++k) {
+            out[(size_t)k * G.pitch + a] = v0;
+            if (two) out[(size_t)k * G.pitch + a + 1] = v1;
+        }
+    }
+    if (rb == G.h) {
+        const size_t last = (size_t)(G.h - 1 - G.row_lo + HALO);
+        const TOUT *src = out + last * G.pitch + a;
+        const TOUT v0 = __ldcg(src), v1 = two ? __ldcg(src + 1) : v0;
+        for (int k = 1; k <= HALO; ++k) {
+            out[(last + k) * G.pitch + a] = v0;
+            if (two) out[(last + k) * G.pitch + a + 1] = v1;
+        }
+    }
+}
+
 // P2P multi-GPU: the slab's first / last HALO rows are the neighbours' halo rows.  Read back what this warp just
 // wrote and store it into the neighbour's output buffer; the LAST boundary CTA of the launch then raises the
 // neighbour's flag (st.release.sys after system fences), which pm_wait_kernel polls before the next launch.
@@ -339,12 +391,15 @@ __global__ void __launch_bounds__(CTA_THREADS, PM_MIN_CTAS) pm_step_kernel(const
     const double K = A.K, L = A.L;
     const double inv_k2 = A.inv_k2, lq = L * 0.25;
     // CTAs whose stencils stay inside the image take the fast path (all but the outermost ring)
-    const bool interior = !STRICT && cb >= 1 && (cb + 1) * PM_CB + 2 <= w && ra >= 2 && rb <= h - 2;
+    const bool interior = !STRICT && cb >= 1 && (cb + 1) * PM_CB + 2 <= w;  // image top/bottom included (replicated halo rows)
     if (interior) {
-        pm_rows_fast<TIN, TOUT>(in, out, G, ra, rb, a, lane, inv_k2, lq);
+        pm_rows_fast<TIN, TOUT, false>(in, out, G, ra, rb, a, lane, inv_k2, lq);
+    } else if (!STRICT) {
+        pm_rows_fast<TIN, TOUT, true>(in, out, G, ra, rb, a, lane, inv_k2, lq);
     } else {
         pm_rows_generic<TIN, TOUT, STRICT>(in, out, G, ra, rb, a, lane, colok, K, L, inv_k2, lq);
     }
+    if ((ra == 0 || rb == h) && lane >= 1 && lane <= 30 && a < w) pm_replicate_border<TOUT>(out, G, ra, rb, a);
     if (A.cv.p2p) pm_push_boundary<TOUT>(A, out, plane, ra, rb, a, lane);
 }
 
