@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libchan_vese_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "chan_vese_b200.h")
-SOURCES = ["api.cu", "csv_kernels.cu", "pm_kernels.cu"]
+SOURCES = ["api.cu", "csv_kernels.cu", "pm_kernels.cu", "f32_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

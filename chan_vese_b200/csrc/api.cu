@@ -107,6 +107,12 @@ struct Job {
     std::vector<void *> ipc_opened;
     unsigned int pm_seq = 0;
 };
+static inline size_t esz(const Job *j) { return j->prec == CVB_PRECISION_F32 ? sizeof(float) : sizeof(double); }
+static inline bool is_f32(const Job *j) { return j->prec == CVB_PRECISION_F32; }
+// plane `m` of level-set buffer `b` (element size depends on the precision)
+static inline char *u_plane(const Job *j, int b, size_t m) {
+    return reinterpret_cast<char *>(j->d_u[b]) + m * (size_t)j->g.plane_elems * esz(j);
+}
 struct cvb_session : Job {};
 struct cvb_batch : Job {};
 
@@ -447,8 +453,9 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
     if (count <= 0 || (n != 1 && n != 3) || h <= 0 || w <= 0)
         return fail(c, CVB_ERR_INVALID_ARGUMENT, "bad job shape: count=%d n=%d h=%d w=%d (n must be 1 or 3)", count, n, h, w);
-    if (prec != CVB_PRECISION_F64)
-        return fail(c, CVB_ERR_INVALID_ARGUMENT, "only CVB_PRECISION_F64 is implemented in this build");
+    if (prec != CVB_PRECISION_F64 && prec != CVB_PRECISION_F32) return fail(c, CVB_ERR_INVALID_ARGUMENT, "unknown precision");
+    if (prec == CVB_PRECISION_F32 && slab)
+        return fail(c, CVB_ERR_INVALID_ARGUMENT, "the fp32 variant runs whole images and batches, not row slabs");
     if (row_lo < 0 || row_hi > h || row_lo >= row_hi) return fail(c, CVB_ERR_INVALID_ARGUMENT, "bad slab rows [%d,%d)", row_lo, row_hi);
     CU(c, cudaSetDevice(c->device));
     j->ctx = c;
@@ -497,16 +504,16 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     }
     const size_t pe = (size_t)g.plane_elems;
     CU(c, cudaMalloc(&j->d_img, (size_t)count * n * pe));
-    CU(c, cudaMalloc(&j->d_u[0], (size_t)count * pe * sizeof(double)));
-    CU(c, cudaMalloc(&j->d_u[1], (size_t)count * pe * sizeof(double)));
+    CU(c, cudaMalloc(&j->d_u[0], (size_t)count * pe * esz(j)));
+    CU(c, cudaMalloc(&j->d_u[1], (size_t)count * pe * esz(j)));
     CU(c, cudaMalloc(&j->d_state, (size_t)count * sizeof(CsvState)));
     const size_t npart = (size_t)count * g.nseg * g.ncb_csv * WARPS_PER_CTA * NACC;
     CU(c, cudaMalloc(&j->d_partials, npart * sizeof(double)));
     CU(c, cudaMalloc(&j->d_group, 2 * (size_t)NGROUPS * count * NACC * sizeof(double)));
     CU(c, cudaMallocHost(&j->h_state, 2 * (size_t)count * sizeof(CsvState)));
     CU(c, cudaMemsetAsync(j->d_img, 0, (size_t)count * n * pe, c->stream));
-    CU(c, cudaMemsetAsync(j->d_u[0], 0, (size_t)count * pe * sizeof(double), c->stream));
-    CU(c, cudaMemsetAsync(j->d_u[1], 0, (size_t)count * pe * sizeof(double), c->stream));
+    CU(c, cudaMemsetAsync(j->d_u[0], 0, (size_t)count * pe * esz(j), c->stream));
+    CU(c, cudaMemsetAsync(j->d_u[1], 0, (size_t)count * pe * esz(j), c->stream));
     CU(c, cudaMemsetAsync(j->d_state, 0, (size_t)count * sizeof(CsvState), c->stream));
     CU(c, cudaMemsetAsync(j->d_partials, 0, npart * sizeof(double), c->stream));
     CU(c, cudaMemsetAsync(j->d_group, 0, 2 * (size_t)NGROUPS * count * NACC * sizeof(double), c->stream));
@@ -620,19 +627,25 @@ static cvb_status job_upload_levelset(Job *j, int index, const double *u) {
     const Geom &g = j->g;
     const int rows = g.row_hi - g.row_lo;
     const int lo = index < 0 ? 0 : index, hi = index < 0 ? g.count : index + 1;
+    const size_t pbytes = (size_t)g.plane_elems * esz(j);
+    if (is_f32(j) && !j->d_aux) CU(c, cudaMalloc(&j->d_aux, (size_t)g.plane_elems * sizeof(double)));
     for (int m = lo; m < hi; ++m) {
-        double *dst = j->d_u[0] + (size_t)m * g.plane_elems + (size_t)HALO * g.pitch;
         if (m == lo) {
+            // fp64: straight into the plane; fp32: through the fp64 staging plane and a conversion kernel
+            double *dst = (is_f32(j) ? j->d_aux : reinterpret_cast<double *>(u_plane(j, 0, m))) + (size_t)HALO * g.pitch;
             CU(c, cudaMemcpy2DAsync(dst, g.pitch * sizeof(double), u, g.w * sizeof(double), g.w * sizeof(double), rows,
                                     cudaMemcpyHostToDevice, c->stream));
             c->stats.h2d_bytes += (uint64_t)rows * g.w * sizeof(double);
+            if (is_f32(j)) {
+                CU(c, launch_convert_d2f(j->d_aux, reinterpret_cast<float *>(u_plane(j, 0, m)), (size_t)g.plane_elems, c->stream));
+                c->stats.kernel_launches += 1;
+            }
         } else {  // one u0 shared by all images: replicate on the device
-            CU(c, cudaMemcpyAsync(dst, j->d_u[0] + (size_t)lo * g.plane_elems + (size_t)HALO * g.pitch,
-                                  (size_t)rows * g.pitch * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            CU(c, cudaMemcpyAsync(u_plane(j, 0, m), u_plane(j, 0, lo), pbytes, cudaMemcpyDeviceToDevice, c->stream));
         }
     }
-    CU(c, launch_replicate_halo(j->d_u[0] + (size_t)lo * g.plane_elems, (size_t)g.plane_elems * sizeof(double),
-                                (size_t)g.pitch * sizeof(double), hi - lo, rows, g.row_lo == 0, g.row_hi == g.h, c->stream));
+    CU(c, launch_replicate_halo(u_plane(j, 0, lo), pbytes, (size_t)g.pitch * esz(j), hi - lo, rows, g.row_lo == 0,
+                                g.row_hi == g.h, c->stream));
     CU(c, cudaMemsetAsync(j->d_state + lo, 0, (size_t)(hi - lo) * sizeof(CsvState), c->stream));
     CU(c, cudaStreamSynchronize(c->stream));  // the caller may reuse its buffer on return
     return CVB_OK;
@@ -650,7 +663,14 @@ static cvb_status job_download_levelset(Job *j, int index, double *u) {
     TRY(job_fetch_state(j));
     const Geom &g = j->g;
     const int rows = g.row_hi - g.row_lo;
-    const double *src = j->d_u[j->h_state[index].steps_done & 1] + (size_t)index * g.plane_elems + (size_t)HALO * g.pitch;
+    const double *src = reinterpret_cast<const double *>(u_plane(j, j->h_state[index].steps_done & 1, index));
+    if (is_f32(j)) {
+        if (!j->d_aux) CU(c, cudaMalloc(&j->d_aux, (size_t)g.plane_elems * sizeof(double)));
+        CU(c, launch_convert_f2d(reinterpret_cast<const float *>(src), j->d_aux, (size_t)g.plane_elems, c->stream));
+        c->stats.kernel_launches += 1;
+        src = j->d_aux;
+    }
+    src += (size_t)HALO * g.pitch;
     CU(c, cudaMemcpy2DAsync(u, g.w * sizeof(double), src, g.pitch * sizeof(double), g.w * sizeof(double), rows,
                             cudaMemcpyDeviceToHost, c->stream));
     c->stats.d2h_bytes += (uint64_t)rows * g.w * sizeof(double);
@@ -666,9 +686,13 @@ static cvb_status job_mask(Job *j, int index, int invert, uint8_t *mask) {
     const int rows = g.row_hi - g.row_lo;
     // the mask is written into the idle level-set buffer's storage (as bytes), then copied out
     const int cur = j->h_state[index].steps_done & 1;
-    const double *src = j->d_u[cur] + (size_t)index * g.plane_elems + (size_t)HALO * g.pitch;
-    uint8_t *tmp = reinterpret_cast<uint8_t *>(j->d_u[cur ^ 1] + (size_t)index * g.plane_elems);
-    CU(c, launch_mask(src, tmp, rows, g.w, g.pitch, invert, c->stream));
+    uint8_t *tmp = reinterpret_cast<uint8_t *>(u_plane(j, cur ^ 1, index));
+    if (is_f32(j))
+        CU(c, launch_mask_f32(reinterpret_cast<const float *>(u_plane(j, cur, index)) + (size_t)HALO * g.pitch, tmp, rows, g.w,
+                              g.pitch, invert, c->stream));
+    else
+        CU(c, launch_mask(reinterpret_cast<const double *>(u_plane(j, cur, index)) + (size_t)HALO * g.pitch, tmp, rows, g.w,
+                          g.pitch, invert, c->stream));
     c->stats.kernel_launches += 1;
     CU(c, cudaMemcpy2DAsync(mask, g.w, tmp, g.pitch, g.w, rows, cudaMemcpyDeviceToHost, c->stream));
     c->stats.d2h_bytes += (uint64_t)rows * g.w;
@@ -688,11 +712,15 @@ static cvb_status job_init_checkerboard(Job *j) {
     CU(c, cudaMemcpyAsync(j->d_sign, s.data(), s.size(), cudaMemcpyHostToDevice, c->stream));
     c->stats.h2d_bytes += s.size();
     for (int m = 0; m < g.count; ++m) {
-        CU(c, launch_checkerboard(j->d_u[0] + (size_t)m * g.plane_elems, j->d_sign, j->d_sign + g.h, g.row_lo,
-                                  g.row_hi - g.row_lo, g.w, g.pitch, c->stream));
+        if (is_f32(j))
+            CU(c, launch_checkerboard_f32(reinterpret_cast<float *>(u_plane(j, 0, m)), j->d_sign, j->d_sign + g.h, g.row_lo,
+                                          g.row_hi - g.row_lo, g.w, g.pitch, c->stream));
+        else
+            CU(c, launch_checkerboard(reinterpret_cast<double *>(u_plane(j, 0, m)), j->d_sign, j->d_sign + g.h, g.row_lo,
+                                      g.row_hi - g.row_lo, g.w, g.pitch, c->stream));
         c->stats.kernel_launches += 1;
     }
-    CU(c, launch_replicate_halo(j->d_u[0], (size_t)g.plane_elems * sizeof(double), (size_t)g.pitch * sizeof(double), g.count,
+    CU(c, launch_replicate_halo(j->d_u[0], (size_t)g.plane_elems * esz(j), (size_t)g.pitch * esz(j), g.count,
                                 g.row_hi - g.row_lo, g.row_lo == 0, g.row_hi == g.h, c->stream));
     CU(c, cudaMemsetAsync(j->d_state, 0, (size_t)g.count * sizeof(CsvState), c->stream));
     CU(c, cudaStreamSynchronize(c->stream));  // s goes out of scope
@@ -710,7 +738,7 @@ static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *st
     CU(c, cudaSetDevice(c->device));
     const Geom &g = j->g;
     const int nplanes = g.count * g.nch;
-    const size_t bytes = (size_t)nplanes * g.plane_elems * sizeof(double);
+    const size_t bytes = (size_t)nplanes * g.plane_elems * esz(j);
     for (int b = 0; b < (nsteps > 2 ? 2 : 1); ++b)
         if (!j->d_pm[b]) {
             CU(c, cudaMalloc(&j->d_pm[b], bytes));
@@ -739,7 +767,10 @@ static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *st
             }
             A.cv.pm_seq = ++j->pm_seq;
         }
-        CU(c, launch_pm_step(A, first, last, strict, c->stream));
+        if (is_f32(j))
+            CU(c, launch_pm_step_f32(A, first, last, c->stream));
+        else
+            CU(c, launch_pm_step(A, first, last, strict, c->stream));
         c->stats.kernel_launches += 1;
         c->stats.pm_step_launches += 1;
         if (last)
@@ -748,7 +779,10 @@ static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *st
             TRY(exchange_halo(j, j->d_pm[(s - 1) & 1], sizeof(double), nplanes));
     }
     if (nsteps == 1) {  // u8 -> fp64 -> u8: the single step cannot write the plane it reads
-        CU(c, launch_pm_quantise(j->d_pm[0], j->d_img, (size_t)nplanes * g.plane_elems, c->stream));
+        if (is_f32(j))
+            CU(c, launch_quantise_f32(reinterpret_cast<const float *>(j->d_pm[0]), j->d_img, (size_t)nplanes * g.plane_elems, c->stream));
+        else
+            CU(c, launch_pm_quantise(j->d_pm[0], j->d_img, (size_t)nplanes * g.plane_elems, c->stream));
         c->stats.kernel_launches += 1;
         TRY(exchange_halo(j, j->d_img, 1, nplanes));
     }
@@ -774,7 +808,7 @@ static cvb_status check_params(cvb_context *c, const cvb_csv_params *p) {
 // sums of the current level set -> c1/c2 (mode 2) or the full set-up of a run (mode 1)
 static cvb_status job_csv_init(Job *j, const CsvArgs &A, int mode) {
     cvb_context *c = j->ctx;
-    CU(c, launch_csv_init(A, mode, c->stream));
+    CU(c, is_f32(j) ? launch_csv_init_f32(A, mode, c->stream) : launch_csv_init(A, mode, c->stream));
     c->stats.kernel_launches += 1;
     TRY(reduce_across_ranks(j, A, mode));
     return CVB_OK;
@@ -782,7 +816,7 @@ static cvb_status job_csv_init(Job *j, const CsvArgs &A, int mode) {
 static cvb_status job_csv_launch_step(Job *j, const CsvArgs &A, int step_index /* 0-based, for halo parity */) {
     cvb_context *c = j->ctx;
     const bool strict = c->math == CVB_MATH_STRICT;
-    CU(c, launch_csv_step(A, strict, c->stream));
+    CU(c, is_f32(j) ? launch_csv_step_f32(A, c->stream) : launch_csv_step(A, strict, c->stream));
     c->stats.kernel_launches += 1;
     c->stats.csv_step_launches += 1;
     if (A.multi_rank) {
@@ -799,15 +833,16 @@ static cvb_status job_csv_run(Job *j, const cvb_csv_params *p, double tol, int m
     TRY(check_params(c, p));
     CU(c, cudaSetDevice(c->device));
     const Geom &g = j->g;
-    if (frame && (g.count != 1 || j->slab)) return fail(c, CVB_ERR_INVALID_ARGUMENT, "frame observer needs a whole single image");
+    if (frame && (g.count != 1 || j->slab || is_f32(j)))
+        return fail(c, CVB_ERR_INVALID_ARGUMENT, "frame observer needs a whole single fp64 image");
     CsvArgs A;
     fill_args(j, p, tol, A);
     // a run starts from the level set in buffer (steps_done & 1); move it to buffer 0 if needed
     TRY(job_fetch_state(j));
     for (int m = 0; m < g.count; ++m)
         if (j->h_state[m].steps_done & 1)
-            CU(c, cudaMemcpyAsync(j->d_u[0] + (size_t)m * g.plane_elems, j->d_u[1] + (size_t)m * g.plane_elems,
-                                  (size_t)g.plane_elems * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            CU(c, cudaMemcpyAsync(u_plane(j, 0, m), u_plane(j, 1, m), (size_t)g.plane_elems * esz(j), cudaMemcpyDeviceToDevice,
+                                  c->stream));
     if (A.multi_rank) TRY(exchange_halo(j, j->d_u[0], sizeof(double), g.count));
     TRY(job_csv_init(j, A, 1));
     const long long limit = max_steps < 0 ? (long long)INT_MAX : (long long)max_steps;  // :890

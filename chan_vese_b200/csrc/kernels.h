@@ -27,4 +27,15 @@ cudaError_t launch_pm_step(const PmArgs &A, bool in_u8, bool out_u8, bool strict
 cudaError_t launch_pm_wait(const CommBox *box, unsigned int need, int has_up, int has_dn, cudaStream_t s);
 cudaError_t launch_pm_quantise(const double *in, uint8_t *out, size_t n, cudaStream_t s);
 
+// fp32 variant (f32_kernels.cu)
+cudaError_t launch_csv_step_f32(const CsvArgs &A, cudaStream_t s);
+cudaError_t launch_csv_init_f32(const CsvArgs &A, int final_mode, cudaStream_t s);
+cudaError_t launch_pm_step_f32(const PmArgs &A, bool in_u8, bool out_u8, cudaStream_t s);
+cudaError_t launch_convert_d2f(const double *in, float *out, size_t n, cudaStream_t s);
+cudaError_t launch_convert_f2d(const float *in, double *out, size_t n, cudaStream_t s);
+cudaError_t launch_mask_f32(const float *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s);
+cudaError_t launch_checkerboard_f32(float *u, const signed char *si, const signed char *sj, int row_lo, int rows, int w,
+                                    int pitch, cudaStream_t s);
+cudaError_t launch_quantise_f32(const float *in, uint8_t *out, size_t n, cudaStream_t s);
+
 }  // namespace cvb

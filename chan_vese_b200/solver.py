@@ -213,16 +213,17 @@ def _wrap_frame(frame, h, w):
 class Session:
     """One image (or one row slab [row_lo, row_hi) of it) resident in HBM."""
 
-    def __init__(self, ctx, n, h, w, rows=None):
+    def __init__(self, ctx, n, h, w, rows=None, fp32=False):
         self.ctx, self.n, self.h, self.w = ctx, n, h, w
         self._lib = ctx._lib
         hd = C.c_void_p()
+        prec = _ffi.PRECISION_F32 if fp32 else _ffi.PRECISION_F64
         if rows is None:
-            ctx.check(self._lib.cvb_session_create(ctx._h, n, h, w, _ffi.PRECISION_F64, C.byref(hd)))
+            ctx.check(self._lib.cvb_session_create(ctx._h, n, h, w, prec, C.byref(hd)))
             self.row_lo, self.row_hi = 0, h
         else:
             self.row_lo, self.row_hi = rows
-            ctx.check(self._lib.cvb_session_create_slab(ctx._h, n, h, w, rows[0], rows[1], _ffi.PRECISION_F64, C.byref(hd)))
+            ctx.check(self._lib.cvb_session_create_slab(ctx._h, n, h, w, rows[0], rows[1], prec, C.byref(hd)))
         self._h = hd
         self.rows = self.row_hi - self.row_lo
 
@@ -310,11 +311,12 @@ class Session:
 class Batch:
     """A batch of independent equal-sized images resident in HBM (no communication between them)."""
 
-    def __init__(self, ctx, count, n, h, w):
+    def __init__(self, ctx, count, n, h, w, fp32=False):
         self.ctx, self.count, self.n, self.h, self.w = ctx, count, n, h, w
         self._lib = ctx._lib
         hd = C.c_void_p()
-        ctx.check(self._lib.cvb_batch_create(ctx._h, count, n, h, w, _ffi.PRECISION_F64, C.byref(hd)))
+        ctx.check(self._lib.cvb_batch_create(ctx._h, count, n, h, w, _ffi.PRECISION_F32 if fp32 else _ffi.PRECISION_F64,
+                                             C.byref(hd)))
         self._h = hd
 
     def close(self):

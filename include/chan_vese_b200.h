@@ -41,8 +41,9 @@ typedef enum cvb_status {
 
 typedef enum cvb_precision {
     CVB_PRECISION_F64 = 0, /* default; the reference's arithmetic type */
-    CVB_PRECISION_F32 = 1  /* level set / PM state in fp32, reductions in fp64; reported separately
-                              (reserved: this build returns CVB_ERR_INVALID_ARGUMENT for it) */
+    CVB_PRECISION_F32 = 1  /* level set / PM state stored and computed in fp32, reductions in fp64; reported
+                              separately (judged on the mask, not on the fp64 level-set tolerance); whole images
+                              and batches only, host buffers stay fp64 */
 } cvb_precision;
 
 typedef enum cvb_math_mode {

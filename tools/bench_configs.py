@@ -28,6 +28,9 @@ def timed(fn, reps, stream):
     return e0.elapsed_time(e1) / reps, out
 
 
+FP32 = os.environ.get("CVB_FP32", "0") == "1"  # the fp32 variant, reported separately
+
+
 def main():
     which = sys.argv[1:] or ["C1", "C2", "C3", "C5"]
     stream = torch.cuda.Stream()
@@ -44,7 +47,7 @@ def main():
             count = int(os.environ.get("C5_COUNT", "4096"))
             base = synth.batch_images(0, 64, h, w)
             imgs = np.ascontiguousarray(np.tile(base, (count // 64, 1, 1, 1)))
-            job = cv.Batch(ctx, count, n, h, w)
+            job = cv.Batch(ctx, count, n, h, w, fp32=FP32)
             job.upload_images(imgs)
             job.save_images()
 
@@ -63,7 +66,7 @@ def main():
             job.close()
         else:
             img = {"C1": synth.seastar, "C2": synth.night_lights, "C3": synth.two_phase}[name]()
-            sess = cv.Session(ctx, n, h, w)
+            sess = cv.Session(ctx, n, h, w, fp32=FP32)
             sess.upload_image(img)
             sess.save_image()
             u0 = cv.levelset_circ(h, w, w // 2, h // 2, h // 4) if c["init"] == "circ" else None
@@ -85,8 +88,8 @@ def main():
             pm_ms = st["pm_ms"] / reps / max(npm, 1)
             res[name] = dict(pm_steps=npm, csv_steps=steps, ms=ms, pixel_iters_per_s=float(h) * w * (npm + steps) / (ms * 1e-3),
                              csv_us_per_step=csv_ms * 1e3, pm_us_per_step=pm_ms * 1e3,
-                             csv_frac_hbm=(16 + n) * h * w / (csv_ms * 1e-3) / 1e9 / PEAK if steps else None,
-                             pm_frac_hbm=16 * n * h * w / (pm_ms * 1e-3) / 1e9 / PEAK if npm else None)
+                             csv_frac_hbm=((8 if FP32 else 16) + n) * h * w / (csv_ms * 1e-3) / 1e9 / PEAK if steps else None,
+                             pm_frac_hbm=(8 if FP32 else 16) * n * h * w / (pm_ms * 1e-3) / 1e9 / PEAK if npm else None)
             sess.close()
         print(name, json.dumps(res[name]), flush=True)
     ctx.close()
