@@ -556,11 +556,7 @@ static void fill_args(const Job *j, const cvb_csv_params *p, double tol, CsvArgs
 static cvb_status reduce_across_ranks(Job *j, const CsvArgs &A, int mode) {
     cvb_context *c = j->ctx;
     if (!A.multi_rank) return CVB_OK;
-    if (j->p2p) {  // the kernel pushed its group sums to the peers: one warp waits for all ranks and folds
-        CU(c, launch_csv_finalize(A, mode, c->stream));
-        c->stats.kernel_launches += 1;
-        return CVB_OK;
-    }
+    if (j->p2p) return CVB_OK;  // the kernel pushed its group sums to the peers, waited for theirs and folded
     const size_t per_rank = (size_t)(NGROUPS / c->nranks) * j->g.count * NACC;
     NC(c, g_nccl.AllGather(j->d_group + per_rank * c->rank, j->d_group, per_rank, ncclFloat64, c->comm, c->stream));
     CU(c, launch_csv_finalize(A, mode, c->stream));
@@ -813,8 +809,9 @@ static cvb_status job_csv_init(Job *j, const CsvArgs &A, int mode) {
     TRY(reduce_across_ranks(j, A, mode));
     return CVB_OK;
 }
-static cvb_status job_csv_launch_step(Job *j, const CsvArgs &A, int step_index /* 0-based, for halo parity */) {
+static cvb_status job_csv_launch_step(Job *j, CsvArgs &A, int step_index /* 0-based: parity of the input buffer */) {
     cvb_context *c = j->ctx;
+    A.par = step_index & 1;
     const bool strict = c->math == CVB_MATH_STRICT;
     CU(c, is_f32(j) ? launch_csv_step_f32(A, c->stream) : launch_csv_step(A, strict, c->stream));
     c->stats.kernel_launches += 1;

@@ -100,6 +100,8 @@ struct CsvArgs {
     double lambda1[MAX_CH], lambda2[MAX_CH];
     double tol;
     int multi_rank;         // 1: stop after the group sums; csv_finalize runs after the all-gather
+    int par;                // parity of the step counter of every image that is still running (known to the host, so
+                            // the first row loads need not wait for the state load); frozen images exit anyway
     int ngroups_local;      // non-empty groups owned by this rank
     int group_lo, group_hi; // groups owned by this rank
     Geom g;

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     if (MODE == MODE_STEP && ds.x) return;  // frozen image: the launch is a no-op (src/main.cpp:1000)
     __syncwarp();
 
-    const int par = ds.y & 1;
+    const int par = (MODE == MODE_STEP) ? A.par : (ds.y & 1);
     const double *__restrict__ uin = A.u[par] + (size_t)img * G.plane_elems;
     double *__restrict__ uout = (MODE == MODE_KAPPA ? A.kappa_out : A.u[par ^ 1]) + (size_t)img * G.plane_elems;
     const uint8_t *__restrict__ im = A.img + (size_t)img * G.nch * G.plane_elems;

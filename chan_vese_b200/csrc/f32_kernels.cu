@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 16) csv_step_f32_kernel(const __g
     CsvState *st = A.state + img;
     const int2 ds = *reinterpret_cast<const int2 *>(&st->done);
     if (ds.x) return;
-    const int par = ds.y & 1;
+    const int par = A.par;
     const float *uin = reinterpret_cast<const float *>(A.u[par]) + (size_t)img * G.plane_elems;
     float *uout = reinterpret_cast<float *>(A.u[par ^ 1]) + (size_t)img * G.plane_elems;
     const uint8_t *im = A.img + (size_t)img * G.nch * G.plane_elems;

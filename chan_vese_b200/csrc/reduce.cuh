@@ -6,9 +6,9 @@
 //   * single GPU: FOLDS the reduction at once -- adds the NGROUPS group sums with a fixed shuffle tree (lane = group)
 //     and updates CsvState (c1/c2, norm, stop flag, step counter) in device memory; or
 //   * multi-GPU row slabs (P2P): copies this rank's group sums into every peer's group-sum array over NVLink and
-//     bumps arrive[rank] in every peer's CommBox (st.release.sys after a system fence).  A one-warp kernel
-//     (csv_wait_fold_kernel) between two step launches waits until all ranks have arrived and folds -- the same
-//     numbers in the same order on every rank => bit-identical c1/c2 and stop decision everywhere.
+//     bumps arrive[rank] in every peer's CommBox (st.release.sys after a system fence), then waits -- one warp, in
+//     the tail of the same launch -- until all ranks have arrived and folds: the same numbers in the same order on
+//     every rank => bit-identical c1/c2 and stop decision everywhere.  (csv_wait_fold remains for completeness.)
 // Groups are keyed to GLOBAL segment indices, so a slab run over 1/2/4/8 GPUs adds exactly the same numbers in
 // exactly the same order as the single-GPU run.  No floating-point atomics anywhere.
 #pragma once
@@ -181,6 +181,16 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
         *reinterpret_cast<volatile unsigned int *>(&A.cv.box->produced) = prod;
     }
     if (lane < A.cv.nranks) st_release_sys(&A.cv.peer_box[lane]->arrive[A.cv.rank], prod);
+    // ... and fold right here, in the tail of the same launch: this one warp waits until every rank has arrived (the
+    // other SMs of this GPU are idle by now; the peers only need THEIR OWN launch to finish, so nobody waits in a
+    // circle), then adds the group sums -- the same numbers in the same order on every rank.  No extra launch per step.
+    if (lane < A.cv.nranks)
+        while (ld_acquire_sys(&A.cv.box->arrive[lane]) < prod) {
+        }
+    __syncwarp();
+    __threadfence_system();
+    csv_fold(A, 0, final_mode, prod);
+    if (lane == 0) A.cv.box->finalized = prod;
 }
 
 }  // namespace cvb
