@@ -180,7 +180,7 @@ def run_b200(args):
     pinned = [torch.empty((rows, w), dtype=torch.uint8).pin_memory() for _ in range(3)]
     views = [p.numpy() for p in pinned]
     synth.hashed_scene_rows(h, w, lo, hi, out=views, threads=min(8, os.cpu_count() or 1))
-    mask_pin = torch.empty((rows, w), dtype=torch.uint8).pin_memory()
+    mask_pin = torch.empty((rows, (w + 7) // 8), dtype=torch.uint8).pin_memory()
     mask_view = mask_pin.numpy()
     prm = cv.make_params()
     sess.upload_image(views)
@@ -194,11 +194,12 @@ def run_b200(args):
         return n_pm, n_csv
 
     def step_e2e():
-        sess.upload_image(views)
+        # host buffers in, host buffer out: planes uploaded from pinned memory (later planes behind the diffusion of
+        # the earlier ones), the segmentation mask read back bit-packed
+        n_pm = sess.upload_image_smooth(views, PM["K"], PM["L"], PM["T"])
         sess.init_checkerboard()
-        n_pm = sess.perona_malik(PM["K"], PM["L"], PM["T"])
         n_csv, _ = sess.csv_run(prm, tol=0.0, max_steps=CSV_STEPS)
-        sess.mask(out=mask_view)
+        sess.mask_packed(out=mask_view)
         return n_pm, n_csv
 
     def barrier():

@@ -74,6 +74,8 @@ SIGNATURES = {
     "cvb_session_download_levelset": (C.c_int, [vp, f64p]),
     "cvb_session_download_image": (C.c_int, [vp, u8pp]),
     "cvb_session_mask": (C.c_int, [vp, C.c_int, u8p]),
+    "cvb_session_mask_packed": (C.c_int, [vp, C.c_int, u8p]),
+    "cvb_session_upload_image_smooth": (C.c_int, [vp, u8pp, C.c_double, C.c_double, C.c_double, intp]),
     "cvb_session_save_image": (C.c_int, [vp]),
     "cvb_session_restore_image": (C.c_int, [vp]),
     "cvb_session_release_scratch": (C.c_int, [vp]),
@@ -90,6 +92,8 @@ SIGNATURES = {
     "cvb_batch_download_levelset": (C.c_int, [vp, C.c_int, f64p]),
     "cvb_batch_download_image": (C.c_int, [vp, C.c_int, u8pp]),
     "cvb_batch_mask": (C.c_int, [vp, C.c_int, C.c_int, u8p]),
+    "cvb_batch_mask_packed": (C.c_int, [vp, C.c_int, C.c_int, u8p]),
+    "cvb_batch_upload_images_smooth": (C.c_int, [vp, u8pp, C.c_double, C.c_double, C.c_double, intp]),
     "cvb_batch_save_images": (C.c_int, [vp]),
     "cvb_batch_restore_images": (C.c_int, [vp]),
     "cvb_batch_release_scratch": (C.c_int, [vp]),

@@ -78,6 +78,8 @@ struct cvb_context {
     cvb_stats stats{};
     double *d_atan_tab = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;  // host-to-device copies overlapped with compute (upload_image_smooth)
+    cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // multi-GPU
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -319,6 +321,9 @@ extern "C" void cvb_context_destroy(cvb_context *c) {
     cudaFree(c->d_atan_tab);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : c->copy_ev)
+        if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -696,6 +701,25 @@ static cvb_status job_mask(Job *j, int index, int invert, uint8_t *mask) {
     return CVB_OK;
 }
 
+// bit-packed mask (MSB first within a byte, rows padded to whole bytes): 1/8 of the device-to-host traffic
+static cvb_status job_mask_packed(Job *j, int index, int invert, uint8_t *bits) {
+    cvb_context *c = j->ctx;
+    if (!bits || index < 0 || index >= j->g.count) return fail(c, CVB_ERR_INVALID_ARGUMENT, "bad mask arguments");
+    CU(c, cudaSetDevice(c->device));
+    TRY(job_fetch_state(j));
+    const Geom &g = j->g;
+    const int rows = g.row_hi - g.row_lo, wb = (g.w + 7) / 8;
+    const int cur = j->h_state[index].steps_done & 1;
+    uint8_t *tmp = reinterpret_cast<uint8_t *>(u_plane(j, cur ^ 1, index));
+    CU(c, launch_mask_packed(u_plane(j, cur, index) + (size_t)HALO * g.pitch * esz(j), is_f32(j) ? 1 : 0, tmp, rows, g.w, g.pitch,
+                             invert, c->stream));
+    c->stats.kernel_launches += 1;
+    CU(c, cudaMemcpyAsync(bits, tmp, (size_t)rows * wb, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += (uint64_t)rows * wb;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
+}
+
 static cvb_status job_init_checkerboard(Job *j) {
     cvb_context *c = j->ctx;
     CU(c, cudaSetDevice(c->device));
@@ -724,35 +748,27 @@ static cvb_status job_init_checkerboard(Job *j) {
 }
 
 // perona_malik, src/main.cpp:478-560, on the resident image planes (in place)
-static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *steps) {
+// nsteps PM launches on planes [plane0, plane0 + np) of the resident image (no timing, no synchronisation)
+static cvb_status pm_run_planes(Job *j, int plane0, int np, double K, double L, int nsteps) {
     cvb_context *c = j->ctx;
-    if (!(L > 0.0) || !(K != 0.0)) return fail(c, CVB_ERR_INVALID_ARGUMENT, "perona_malik needs L > 0 and K != 0");
-    const int nsteps = cvb_pm_num_steps(L, T);
-    if (nsteps < 0) return fail(c, CVB_ERR_INVALID_ARGUMENT, "perona_malik step count overflows");
-    if (steps) *steps = nsteps;
-    if (nsteps == 0) return CVB_OK;  // the reference returns an unset image here; the planes are left unchanged
-    CU(c, cudaSetDevice(c->device));
     const Geom &g = j->g;
-    const int nplanes = g.count * g.nch;
-    const size_t bytes = (size_t)nplanes * g.plane_elems * esz(j);
-    for (int b = 0; b < (nsteps > 2 ? 2 : 1); ++b)
-        if (!j->d_pm[b]) {
-            CU(c, cudaMalloc(&j->d_pm[b], bytes));
-            CU(c, cudaMemsetAsync(j->d_pm[b], 0, bytes, c->stream));
-        }
     const bool strict = c->math == CVB_MATH_STRICT;
+    const size_t poff = (size_t)plane0 * g.plane_elems;
     PmArgs A;
     memset(&A, 0, sizeof A);
     A.K = K;
     A.L = L;
     A.inv_k2 = 1.0 / (K * K);
     A.g = g;
+    A.g.count = 1;  // the PM kernels only use count * nch = number of planes
+    A.g.nch = np;
     A.cv = j->cv;
-    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    uint8_t *img = j->d_img + poff;
+    char *pm[2] = {reinterpret_cast<char *>(j->d_pm[0]) + poff * esz(j), reinterpret_cast<char *>(j->d_pm[1]) + poff * esz(j)};
     for (int s = 1; s <= nsteps; ++s) {
         const bool first = s == 1, last = s == nsteps && nsteps >= 2;
-        A.in = first ? (const void *)j->d_img : (const void *)j->d_pm[(s - 2) & 1];
-        A.out = last ? (void *)j->d_img : (void *)j->d_pm[(s - 1) & 1];
+        A.in = first ? (const void *)img : (const void *)pm[(s - 2) & 1];
+        A.out = last ? (void *)img : (void *)pm[(s - 1) & 1];
         A.out_buf = last ? -1 : ((s - 1) & 1);
         if (j->p2p) {
             // boundary rows travel inside the kernel (stores into the neighbours' halos + a flag); before a launch
@@ -770,23 +786,98 @@ static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *st
         c->stats.kernel_launches += 1;
         c->stats.pm_step_launches += 1;
         if (last)
-            TRY(exchange_halo(j, j->d_img, 1, nplanes));
+            TRY(exchange_halo(j, img, 1, np));
         else if (s < nsteps && !j->p2p)
-            TRY(exchange_halo(j, j->d_pm[(s - 1) & 1], sizeof(double), nplanes));
+            TRY(exchange_halo(j, pm[(s - 1) & 1], sizeof(double), np));
     }
     if (nsteps == 1) {  // u8 -> fp64 -> u8: the single step cannot write the plane it reads
         if (is_f32(j))
-            CU(c, launch_quantise_f32(reinterpret_cast<const float *>(j->d_pm[0]), j->d_img, (size_t)nplanes * g.plane_elems, c->stream));
+            CU(c, launch_quantise_f32(reinterpret_cast<const float *>(pm[0]), img, (size_t)np * g.plane_elems, c->stream));
         else
-            CU(c, launch_pm_quantise(j->d_pm[0], j->d_img, (size_t)nplanes * g.plane_elems, c->stream));
+            CU(c, launch_pm_quantise(reinterpret_cast<const double *>(pm[0]), img, (size_t)np * g.plane_elems, c->stream));
         c->stats.kernel_launches += 1;
-        TRY(exchange_halo(j, j->d_img, 1, nplanes));
+        TRY(exchange_halo(j, img, 1, np));
     }
+    return CVB_OK;
+}
+static cvb_status pm_prepare(Job *j, double K, double L, double T, int *steps, int *nsteps_out) {
+    cvb_context *c = j->ctx;
+    if (!(L > 0.0) || !(K != 0.0)) return fail(c, CVB_ERR_INVALID_ARGUMENT, "perona_malik needs L > 0 and K != 0");
+    const int nsteps = cvb_pm_num_steps(L, T);
+    if (nsteps < 0) return fail(c, CVB_ERR_INVALID_ARGUMENT, "perona_malik step count overflows");
+    if (steps) *steps = nsteps;
+    *nsteps_out = nsteps;
+    if (nsteps == 0) return CVB_OK;
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    const size_t bytes = (size_t)g.count * g.nch * g.plane_elems * esz(j);
+    for (int b = 0; b < (nsteps > 2 ? 2 : 1); ++b)
+        if (!j->d_pm[b]) {
+            CU(c, cudaMalloc(&j->d_pm[b], bytes));
+            CU(c, cudaMemsetAsync(j->d_pm[b], 0, bytes, c->stream));
+        }
+    return CVB_OK;
+}
+
+// perona_malik, src/main.cpp:478-560, on the resident image planes (in place)
+static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *steps) {
+    cvb_context *c = j->ctx;
+    int nsteps = 0;
+    TRY(pm_prepare(j, K, L, T, steps, &nsteps));
+    if (nsteps == 0) return CVB_OK;  // the reference returns an unset image here; the planes are left unchanged
+    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    TRY(pm_run_planes(j, 0, j->g.count * j->g.nch, K, L, nsteps));
     CU(c, cudaEventRecord(c->ev[1], c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     c->stats.pm_ms += ms;
+    return CVB_OK;
+}
+
+// upload_image + perona_malik with the host-to-device copies hidden behind the diffusion of the planes that have
+// already arrived (channels diffuse independently, src/main.cpp:489): planes go up in chunks on a copy stream, each
+// chunk's PM launches wait only for that chunk's copy.
+static cvb_status job_upload_image_smooth(Job *j, const uint8_t *const *planes, double K, double L, double T, int *steps) {
+    cvb_context *c = j->ctx;
+    if (!planes) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes is NULL");
+    const Geom &g = j->g;
+    const int nplanes = g.count * g.nch;
+    int nsteps = 0;
+    TRY(pm_prepare(j, K, L, T, steps, &nsteps));
+    if (j->slab || nsteps == 0 || nplanes < 2) {  // nothing to overlap (or halo exchanges in the way): the plain sequence
+        TRY(job_upload_image(j, planes));
+        return nsteps ? job_perona_malik(j, K, L, T, nullptr) : CVB_OK;
+    }
+    if (!c->copy_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : c->copy_ev) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int rows = g.row_hi - g.row_lo;
+    const int nchunk = std::min(nplanes, 4);
+    // the copy stream must not overwrite planes the compute stream may still be using
+    CU(c, cudaEventRecord(c->copy_ev[4], c->stream));
+    CU(c, cudaStreamWaitEvent(c->copy_stream, c->copy_ev[4], 0));
+    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    float pm_ms = 0;
+    for (int k = 0; k < nchunk; ++k) {
+        const int p0 = (int)((long long)nplanes * k / nchunk), p1 = (int)((long long)nplanes * (k + 1) / nchunk);
+        for (int p = p0; p < p1; ++p) {
+            if (!planes[p]) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes[%d] is NULL", p);
+            CU(c, cudaMemcpy2DAsync(j->d_img + (size_t)p * g.plane_elems + (size_t)HALO * g.pitch, g.pitch, planes[p], g.w, g.w,
+                                    rows, cudaMemcpyHostToDevice, c->copy_stream));
+            c->stats.h2d_bytes += (uint64_t)rows * g.w;
+        }
+        CU(c, cudaEventRecord(c->copy_ev[k], c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->copy_ev[k], 0));
+        CU(c, launch_replicate_halo(j->d_img + (size_t)p0 * g.plane_elems, (size_t)g.plane_elems, (size_t)g.pitch, p1 - p0, rows,
+                                    g.row_lo == 0, g.row_hi == g.h, c->stream));
+        TRY(pm_run_planes(j, p0, p1 - p0, K, L, nsteps));
+    }
+    CU(c, cudaEventRecord(c->ev[1], c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&pm_ms, c->ev[0], c->ev[1]);
+    c->stats.pm_ms += pm_ms;  // includes the exposed part of the copies
     return CVB_OK;
 }
 static void job_release_pm(Job *j) {
@@ -1095,6 +1186,13 @@ extern "C" cvb_status cvb_session_download_image(cvb_session *s, uint8_t *const 
 extern "C" cvb_status cvb_session_mask(cvb_session *s, int invert, uint8_t *mask) {
     return s ? job_mask(s, 0, invert, mask) : CVB_ERR_INVALID_ARGUMENT;
 }
+extern "C" cvb_status cvb_session_mask_packed(cvb_session *s, int invert, uint8_t *bits) {
+    return s ? job_mask_packed(s, 0, invert, bits) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_session_upload_image_smooth(cvb_session *s, const uint8_t *const *planes, double K, double L, double T,
+                                                      int *steps) {
+    return s ? job_upload_image_smooth(s, planes, K, L, T, steps) : CVB_ERR_INVALID_ARGUMENT;
+}
 extern "C" cvb_status cvb_session_save_image(cvb_session *s) { return s ? job_save_image(s) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_session_restore_image(cvb_session *s) { return s ? job_restore_image(s) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_session_release_scratch(cvb_session *s) {
@@ -1149,6 +1247,13 @@ extern "C" cvb_status cvb_batch_download_image(cvb_batch *b, int index, uint8_t 
 }
 extern "C" cvb_status cvb_batch_mask(cvb_batch *b, int index, int invert, uint8_t *mask) {
     return b ? job_mask(b, index, invert, mask) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_mask_packed(cvb_batch *b, int index, int invert, uint8_t *bits) {
+    return b ? job_mask_packed(b, index, invert, bits) : CVB_ERR_INVALID_ARGUMENT;
+}
+extern "C" cvb_status cvb_batch_upload_images_smooth(cvb_batch *b, const uint8_t *const *planes, double K, double L, double T,
+                                                     int *steps) {
+    return b ? job_upload_image_smooth(b, planes, K, L, T, steps) : CVB_ERR_INVALID_ARGUMENT;
 }
 extern "C" cvb_status cvb_batch_save_images(cvb_batch *b) { return b ? job_save_image(b) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_batch_restore_images(cvb_batch *b) { return b ? job_restore_image(b) : CVB_ERR_INVALID_ARGUMENT; }

@@ -648,6 +648,27 @@ __global__ void mask_kernel(const double *u, uint8_t *mask, int rows, int w, int
     mask[q] = invert ? (uint8_t)(1 - m) : m;
 }
 
+// the same mask, 8 pixels per byte (MSB first), rows padded to whole bytes; u is fp64 or fp32
+__global__ void mask_packed_kernel(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert) {
+    const int jb = blockIdx.x * blockDim.x + threadIdx.x;  // byte within the row
+    const int i = blockIdx.y;
+    const int wb = (w + 7) / 8;
+    if (jb >= wb || i >= rows) return;
+    unsigned int b = 0;
+    for (int k = 0; k < 8; ++k) {
+        const int j = jb * 8 + k;
+        unsigned int m = 0;
+        if (j < w) {
+            const float v = f32 ? reinterpret_cast<const float *>(u)[(size_t)i * pitch + j]
+                                : __double2float_rn(reinterpret_cast<const double *>(u)[(size_t)i * pitch + j]);
+            m = (v > 0.0f) ? 1u : 0u;
+            if (invert) m ^= 1u;
+        }
+        b |= m << (7 - k);
+    }
+    bits[(size_t)i * wb + jb] = (uint8_t)b;
+}
+
 // u0(i,j) = si[i] * sj[j] with host-computed sign vectors (bit parity with glibc sin)
 __global__ void checkerboard_kernel(double *u, const signed char *si, const signed char *sj, int row_lo, int rows,
                                     int w, int pitch) {
@@ -729,6 +750,11 @@ cudaError_t launch_delta_map(double *data, size_t n, double eps, cudaStream_t s)
 cudaError_t launch_mask(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s) {
     dim3 grid((w + 255) / 256, rows);
     mask_kernel<<<grid, 256, 0, s>>>(u, mask, rows, w, pitch, invert);
+    return cudaGetLastError();
+}
+cudaError_t launch_mask_packed(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, cudaStream_t s) {
+    dim3 grid(((w + 7) / 8 + 127) / 128, rows);
+    mask_packed_kernel<<<grid, 128, 0, s>>>(u, f32, bits, rows, w, pitch, invert);
     return cudaGetLastError();
 }
 cudaError_t launch_checkerboard(double *u, const signed char *si, const signed char *sj, int row_lo, int rows, int w,

@@ -15,6 +15,7 @@ cudaError_t launch_csv_init(const CsvArgs &A, int final_mode, cudaStream_t s);
 cudaError_t launch_csv_finalize(const CsvArgs &A, int mode, cudaStream_t s);
 cudaError_t launch_delta_map(double *data, size_t n, double eps, cudaStream_t s);
 cudaError_t launch_mask(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s);
+cudaError_t launch_mask_packed(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, cudaStream_t s);
 // border halo rows := copies of the first / last image row (planes of any element size; row_bytes multiple of 16)
 cudaError_t launch_replicate_halo(void *base, size_t plane_bytes, size_t row_bytes, int nplanes, int rows, int top, int bottom,
                                   cudaStream_t s);

@@ -298,6 +298,20 @@ class Session:
         self.ctx.check(self._lib.cvb_session_mask(self._h, int(bool(invert)), m.ctypes.data_as(_ffi.u8p)))
         return m
 
+    def mask_packed(self, invert=False, out=None):
+        """Bit-packed mask, numpy.packbits layout along each row: (rows, (w+7)//8) uint8."""
+        wb = (self.w + 7) // 8
+        m = out if out is not None else np.empty((self.rows, wb), dtype=np.uint8)
+        self.ctx.check(self._lib.cvb_session_mask_packed(self._h, int(bool(invert)), m.ctypes.data_as(_ffi.u8p)))
+        return m
+
+    def upload_image_smooth(self, channels, K, L, T):
+        """upload_image + perona_malik with the copies hidden behind the diffusion of the planes already there."""
+        arrs, ptrs = _planes(channels, self.rows, self.w)
+        steps = C.c_int(0)
+        self.ctx.check(self._lib.cvb_session_upload_image_smooth(self._h, ptrs, K, L, T, C.byref(steps)))
+        return steps.value
+
     def save_image(self):
         self.ctx.check(self._lib.cvb_session_save_image(self._h))
 

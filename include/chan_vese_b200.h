@@ -170,6 +170,14 @@ cvb_status cvb_session_region_means(cvb_session *s, double eps, double *c1, doub
 cvb_status cvb_session_download_levelset(cvb_session *s, double *u);
 cvb_status cvb_session_download_image(cvb_session *s, uint8_t *const *planes);
 cvb_status cvb_session_mask(cvb_session *s, int invert, uint8_t *mask);
+/* The same mask bit-packed: 8 pixels per byte, MSB first, every row padded to (w+7)/8 bytes (numpy.packbits
+ * layout along the row) -- 1/8 of the device-to-host traffic.  bits: rows * ((w+7)/8) bytes. */
+cvb_status cvb_session_mask_packed(cvb_session *s, int invert, uint8_t *bits);
+/* upload_image followed by perona_malik, with the host-to-device copies of later planes hidden behind the diffusion
+ * of the planes that have already arrived (channels diffuse independently, src/main.cpp:489).  Pinned host memory
+ * (cvb_host_alloc) makes the copies truly asynchronous.  Falls back to the plain sequence for row slabs. */
+cvb_status cvb_session_upload_image_smooth(cvb_session *s, const uint8_t *const *planes, double K, double L, double T,
+                                           int *steps);
 /* Perona-Malik smooths the resident planes in place (as the reference re-splits img at src/main.cpp:945).
  * save_image keeps a device copy of the current planes, restore_image brings it back (device to device). */
 cvb_status cvb_session_save_image(cvb_session *s);
@@ -200,6 +208,8 @@ cvb_status cvb_batch_csv_run(cvb_batch *b, const cvb_csv_params *params, double 
 cvb_status cvb_batch_download_levelset(cvb_batch *b, int index, double *u);
 cvb_status cvb_batch_download_image(cvb_batch *b, int index, uint8_t *const *planes);
 cvb_status cvb_batch_mask(cvb_batch *b, int index, int invert, uint8_t *mask);
+cvb_status cvb_batch_mask_packed(cvb_batch *b, int index, int invert, uint8_t *bits);
+cvb_status cvb_batch_upload_images_smooth(cvb_batch *b, const uint8_t *const *planes, double K, double L, double T, int *steps);
 cvb_status cvb_batch_save_images(cvb_batch *b);
 cvb_status cvb_batch_restore_images(cvb_batch *b);
 cvb_status cvb_batch_release_scratch(cvb_batch *b);

@@ -395,3 +395,21 @@ def test_fp32_variant_gray_ring_and_batch(ctx):
         r = ctx.segment(list(imgs[k]), cv.levelset_checkerboard(96, 112), cv.make_params(), tol=0.0, max_steps=15, smooth=True,
                         K=30.0, L=0.25, T=1.0)
         assert (masks[k] == r["mask"]).mean() >= 0.995
+
+
+def test_overlapped_upload_and_packed_mask(ctx):
+    """cvb_session_upload_image_smooth == upload_image + perona_malik (bit-identical); the packed mask is
+    numpy.packbits of the byte mask."""
+    img = synth.seastar(130, 203, seed=8)
+    with cv.Session(ctx, 3, 130, 203) as s:
+        s.upload_image(img)
+        n1 = s.perona_malik(25.0, 0.25, 2.0)
+        ref = s.download_image()
+        n2 = s.upload_image_smooth(img, 25.0, 0.25, 2.0)
+        got = s.download_image()
+        assert n1 == n2 == 8 and all(np.array_equal(a, b) for a, b in zip(ref, got))
+        s.init_checkerboard()
+        s.csv_run(cv.make_params(), tol=0.0, max_steps=10)
+        m = s.mask()
+        assert np.array_equal(s.mask_packed(), np.packbits(m, axis=1))
+        assert np.array_equal(s.mask_packed(invert=True), np.packbits(1 - m, axis=1))
