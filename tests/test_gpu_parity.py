@@ -413,3 +413,42 @@ def test_overlapped_upload_and_packed_mask(ctx):
         m = s.mask()
         assert np.array_equal(s.mask_packed(), np.packbits(m, axis=1))
         assert np.array_equal(s.mask_packed(invert=True), np.packbits(1 - m, axis=1))
+
+
+def test_error_paths_and_degenerate_shapes(ctx):
+    """Invalid arguments come back as status codes with a message (never a crash, never a CPU result); the smallest
+    shapes the reference accepts (1x1, 1xN, Nx1) run."""
+    import ctypes as C
+    from chan_vese_b200 import _ffi
+    img = [np.zeros((8, 8), np.uint8)] * 2
+    with pytest.raises(cv.ChanVeseError) as e:
+        ctx.perona_malik(img, 10.0, 0.25, 1.0)  # two channels: the reference knows 1 (-g) or 3
+    assert e.value.status == _ffi.ERR_INVALID_ARGUMENT and "n must be 1 or 3" in str(e.value)
+    with pytest.raises(cv.ChanVeseError):
+        ctx.csv_run([np.zeros((8, 8), np.uint8)], np.zeros((8, 8)), cv.make_params(eps=0.0, nch=1), max_steps=1)
+    with pytest.raises(cv.ChanVeseError):
+        ctx.perona_malik([np.zeros((8, 8), np.uint8)], 10.0, 0.0, 1.0)  # L must be > 0
+    lib = _ffi.lib()
+    assert lib.cvb_csv_run(ctx._h, None, 1, 8, 8, None, None, 1e-3, 1, None, None, C.cast(None, _ffi.FRAME_FN), None) != _ffi.OK
+    hd = C.c_void_p()
+    assert lib.cvb_session_create(ctx._h, 1, 0, 8, 0, C.byref(hd)) == _ffi.ERR_INVALID_ARGUMENT
+    assert lib.cvb_session_create_slab(ctx._h, 1, 64, 64, 3, 40, 0, C.byref(hd)) == _ffi.ERR_INVALID_ARGUMENT  # unaligned slab
+    assert b"aligned" in lib.cvb_last_error(ctx._h) or b"split" in lib.cvb_last_error(ctx._h)
+    with pytest.raises(ValueError):
+        cv.Session(ctx, 1, 8, 8).upload_levelset(np.zeros((4, 4)))
+    for h, w in [(1, 1), (1, 7), (9, 1), (2, 3)]:
+        rng = np.random.default_rng(h * 10 + w)
+        im = [rng.integers(0, 256, size=(h, w), dtype=np.uint8)]
+        u0 = rng.standard_normal((h, w))
+        # tol < 0 never stops (the reference lets it through, SURVEY Q9); with tol = 0 a 1x1 image sits on the knife
+        # edge du = 0 <= 0, which rounding decides
+        u, steps, _ = ctx.csv_run(im, u0, cv.make_params(nch=1), tol=-1.0, max_steps=4)
+        ref, rs, _ = co.csv_run(im, u0, co.params(), -1.0, 4)
+        assert steps == rs == 4 and rel_l2(u, ref) < 1e-10
+        out, n = ctx.perona_malik(im, 10.0, 0.25, 1.0)
+        refp, _ = co.perona_malik(im, 10.0, 0.25, 1.0)
+        assert n == 4 and np.abs(out[0].astype(int) - refp[0].astype(int)).max() <= 1
+    # max_steps = 0: nothing runs, u comes back unchanged
+    u0 = np.arange(64.0).reshape(8, 8)
+    u, steps, _ = ctx.csv_run([np.zeros((8, 8), np.uint8)], u0, cv.make_params(nch=1), tol=0.0, max_steps=0)
+    assert steps == 0 and np.array_equal(u, u0)

@@ -33,8 +33,15 @@ FP32 = os.environ.get("CVB_FP32", "0") == "1"  # the fp32 variant, reported sepa
 
 def main():
     which = sys.argv[1:] or ["C1", "C2", "C3", "C5"]
+    # C5 across GPUs (torchrun): images are independent, every rank takes count / world of them, no communication
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        which = ["C5"]
     stream = torch.cuda.Stream()
-    ctx = cv.Context(0, stream=stream.cuda_stream)
+    ctx = cv.Context(local, stream=stream.cuda_stream)
     res = {}
     for name in which:
         c = synth.CONFIGS[name]
@@ -44,7 +51,8 @@ def main():
         tol = k.pop("tol", 1e-3)
         prm = cv.make_params(nch=n, **k)
         if name == "C5":
-            count = int(os.environ.get("C5_COUNT", "4096"))
+            total = int(os.environ.get("C5_COUNT", "4096"))
+            count = total // world
             base = synth.batch_images(0, 64, h, w)
             imgs = np.ascontiguousarray(np.tile(base, (count // 64, 1, 1, 1)))
             job = cv.Batch(ctx, count, n, h, w, fp32=FP32)
@@ -61,7 +69,13 @@ def main():
             ms, (npm, steps) = timed(run, 2, stream)
             st = ctx.stats()
             pixit = float(h) * w * (npm * count + int(steps.sum()))
-            res[name] = dict(images=count, pm_steps=npm, csv_steps_mean=float(steps.mean()), csv_steps_min=int(steps.min()),
+            if world > 1:  # whole-job throughput: all ranks' pixel-iterations over the slowest rank's time
+                t = torch.tensor([ms, pixit], dtype=torch.float64, device="cuda")
+                tmax = t.clone()
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                ms, pixit = float(tmax[0]), float(t[1])
+            res[name] = dict(images=count * world, gpus=world, pm_steps=npm, csv_steps_mean=float(steps.mean()), csv_steps_min=int(steps.min()),
                              csv_steps_max=int(steps.max()), ms=ms, pixel_iters_per_s=pixit / (ms * 1e-3))
             job.close()
         else:
@@ -91,7 +105,8 @@ def main():
                              csv_frac_hbm=((8 if FP32 else 16) + n) * h * w / (csv_ms * 1e-3) / 1e9 / PEAK if steps else None,
                              pm_frac_hbm=(8 if FP32 else 16) * n * h * w / (pm_ms * 1e-3) / 1e9 / PEAK if npm else None)
             sess.close()
-        print(name, json.dumps(res[name]), flush=True)
+        if rank == 0:
+            print(name, json.dumps(res[name]), flush=True)
     ctx.close()
 
 
