@@ -19,6 +19,11 @@
 
 namespace cvb {
 
+#ifndef CSV_UNROLL
+#define CSV_UNROLL 2
+#endif
+constexpr int kCsvUnroll = CSV_UNROLL;  // unroll factor of the fast-path row loop
+
 #ifndef CSV_D
 #define CSV_D 2
 #endif
@@ -162,7 +167,7 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
 #pragma unroll
     for (int c = 0; c < NCH; ++c) accI[c] = 0.0;
 
-#pragma unroll 2
+#pragma unroll kCsvUnroll
     for (int r = 0; r < n; ++r) {
         const double2 S = q0;
         const double e2s = f0;

@@ -17,6 +17,11 @@
 
 namespace cvb {
 
+#ifndef PM_UNROLL
+#define PM_UNROLL 2
+#endif
+constexpr int kPmUnroll = PM_UNROLL;  // unroll factor of the fast-path row loop
+
 #ifndef PM_D
 #define PM_D 2
 #endif
@@ -150,7 +155,7 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
     double2 q0 = ldr(pin), q1 = make_double2(0.0, 0.0);
     if (n > 1) q1 = ldr(pin + pitch);
     pin += 2 * pitch;  // row ra+4: next row to fetch
-#pragma unroll 2
+#pragma unroll kPmUnroll
     for (int r = 0; r < n; ++r) {
         const double2 X = q0;  // row i+2
         q0 = q1;

@@ -452,3 +452,34 @@ def test_error_paths_and_degenerate_shapes(ctx):
     u0 = np.arange(64.0).reshape(8, 8)
     u, steps, _ = ctx.csv_run([np.zeros((8, 8), np.uint8)], u0, cv.make_params(nch=1), tol=0.0, max_steps=0)
     assert steps == 0 and np.array_equal(u, u0)
+
+
+def test_random_shapes_against_oracle(ctx):
+    """Widths around the 62- and 60-column strip boundaries, odd sizes, heights around the tile lengths, random
+    parameters: CSV (3-6 steps) and PM (2-5 steps) against the oracle."""
+    rng = np.random.default_rng(2024)
+    widths = [2, 3, 59, 60, 61, 62, 63, 64, 65, 119, 120, 121, 123, 124, 125, 126, 185, 186, 187, 247, 248, 249, 250, 311, 373]
+    heights = [2, 3, 4, 5, 7, 8, 9, 31, 33, 47, 48, 49, 50, 97, 130]
+    for case in range(30):
+        w = int(widths[case % len(widths)])
+        h = int(rng.choice(heights))
+        n = int(rng.choice([1, 3]))
+        img = [rng.integers(0, 256, size=(h, w), dtype=np.uint8) for _ in range(n)]
+        u0 = rng.standard_normal((h, w)) * float(rng.choice([0.05, 1.0, 30.0]))
+        lam1 = [float(x) for x in rng.uniform(0.2, 2.0, n)] if case % 2 else [1.0] * n
+        lam2 = [float(x) for x in rng.uniform(0.2, 2.0, n)] if case % 2 else [1.0] * n
+        kw = dict(mu=float(rng.uniform(0, 1)), nu=float(rng.uniform(-1, 1)), dt=float(rng.choice([0.1, 1.0])),
+                  eps=float(rng.choice([0.5, 1.0, 2.0])), lambda1=lam1, lambda2=lam2, nch=n)
+        steps = int(rng.integers(3, 7))
+        u, s, nrm = ctx.csv_run(img, u0, cv.make_params(**kw), tol=-1.0, max_steps=steps)
+        ref, rs, rn = co.csv_run(img, u0, co.params(**kw), -1.0, steps)
+        assert s == rs == steps, (case, h, w, n)
+        assert rel_l2(u, ref) < 1e-9, (case, h, w, n, rel_l2(u, ref))
+        assert abs(nrm - rn) <= 1e-9 * max(rn, 1e-300), (case, h, w, n)
+        K, L = float(rng.choice([5.0, 30.0])), float(rng.choice([0.1, 0.25]))
+        T = L * int(rng.integers(2, 6)) - L / 2
+        out, npm = ctx.perona_malik(img, K, L, T)
+        refp, nr = co.perona_malik(img, K, L, T)
+        assert npm == nr
+        d = np.abs(np.stack(out).astype(int) - np.stack(refp).astype(int))
+        assert d.max() <= 1 and (d == 0).mean() >= 0.995, (case, h, w, n, d.max(), (d == 0).mean())
