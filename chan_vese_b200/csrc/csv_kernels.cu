@@ -12,6 +12,8 @@
 // is carried from the previous row.  Lane 0 is a halo lane (it supplies nx of the column left of the
 // strip), so a strip owns 62 columns and a 4-warp CTA 248.  Loads run a software pipeline: L2 prefetch
 // CSV_PF rows ahead, register prefetch CSV_D rows ahead.
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "math.cuh"
@@ -308,6 +310,14 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     CsvState *st = A.state + img;
 #pragma unroll
     for (int q = 0; q < ATAN_TAB_N; q += 32) s_tab[q + lane] = A.atan_tab[q + lane];
+#ifndef CSV_NO_PDL
+    if (MODE == MODE_STEP && !STRICT) {
+        // launched with programmatic stream serialization: everything above is independent of the previous launch;
+        // wait for it (c1/c2, stop flag, level set, halo rows), then let the next launch start filling freed slots
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+    }
+#endif
     const int2 ds = *reinterpret_cast<const int2 *>(&st->done);  // {done, steps_done}
     if (MODE == MODE_STEP && ds.x) return;  // frozen image: the launch is a no-op (src/main.cpp:1000)
     __syncwarp();
@@ -721,8 +731,26 @@ static cudaError_t launch_step_n(const CsvArgs &A, bool strict, int mode, cudaSt
     } else {
         if (strict)
             csv_step_kernel<NCH, true, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
-        else
+        else {
+#ifdef CSV_NO_PDL
             csv_step_kernel<NCH, false, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
+#else
+            // Programmatic dependent launch: the CTAs of step n+1 may become resident while the tail of step n (last
+            // wave, group reductions, multi-GPU fold) is still running; they load the atan table and then block in
+            // griddepcontrol.wait until step n has completed and flushed.
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(CTA_THREADS);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, csv_step_kernel<NCH, false, MODE_STEP>, A);
+#endif
+        }
     }
     return cudaGetLastError();
 }

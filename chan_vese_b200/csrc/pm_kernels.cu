@@ -10,6 +10,8 @@
 // of I, three rows of the separable Sobel row sums and three rows of g live in registers; west/east
 // neighbours come from warp shuffles.  The stencil has radius 2, so lanes 0 and 31 are halo lanes:
 // a strip owns 60 columns, a 4-warp CTA 240.
+#include <string.h>
+
 #include "comm.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -384,6 +386,10 @@ __global__ void __launch_bounds__(CTA_THREADS, PM_MIN_CTAS) pm_step_kernel(const
     bid /= G.ncb_pm;
     const int seg = bid % G.pm_nseg;
     const int plane = bid / G.pm_nseg;  // image * nch + channel: channels diffuse independently (:489)
+    if (!STRICT) {  // launched with programmatic stream serialization: wait for the previous launch, release the next
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+    }
     const TIN *__restrict__ in = reinterpret_cast<const TIN *>(A.in) + (size_t)plane * G.plane_elems;
     TOUT *__restrict__ out = reinterpret_cast<TOUT *>(A.out) + (size_t)plane * G.plane_elems;
     const int ra = G.row_lo + seg * G.pm_seg_rows;
@@ -419,8 +425,20 @@ static cudaError_t launch_pm_t(const PmArgs &A, bool strict, cudaStream_t s) {
     const unsigned int grid = (unsigned int)((size_t)G.count * G.nch * G.pm_nseg * G.ncb_pm);
     if (strict)
         pm_step_kernel<TIN, TOUT, true><<<grid, CTA_THREADS, 0, s>>>(A);
-    else
-        pm_step_kernel<TIN, TOUT, false><<<grid, CTA_THREADS, 0, s>>>(A);
+    else {
+        // programmatic dependent launch (see csv_kernels.cu): step n+1's CTAs become resident during the tail of step n
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(CTA_THREADS);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, pm_step_kernel<TIN, TOUT, false>, A);
+    }
     return cudaGetLastError();
 }
 
