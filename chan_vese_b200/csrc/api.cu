@@ -763,6 +763,10 @@ static cvb_status pm_run_planes(Job *j, int plane0, int np, double K, double L, 
     A.g.count = 1;  // the PM kernels only use count * nch = number of planes
     A.g.nch = np;
     A.cv = j->cv;
+    for (int b = 0; b < 2; ++b) {  // the kernels index the neighbours' buffers by plane - plane0, like their own
+        if (A.cv.up_pm[b]) A.cv.up_pm[b] += (size_t)plane0 * (size_t)(A.cv.up_rows + 2 * HALO) * g.pitch;
+        if (A.cv.dn_pm[b]) A.cv.dn_pm[b] += (size_t)plane0 * (size_t)(A.cv.dn_rows + 2 * HALO) * g.pitch;
+    }
     uint8_t *img = j->d_img + poff;
     char *pm[2] = {reinterpret_cast<char *>(j->d_pm[0]) + poff * esz(j), reinterpret_cast<char *>(j->d_pm[1]) + poff * esz(j)};
     for (int s = 1; s <= nsteps; ++s) {
@@ -845,7 +849,7 @@ static cvb_status job_upload_image_smooth(Job *j, const uint8_t *const *planes, 
     const int nplanes = g.count * g.nch;
     int nsteps = 0;
     TRY(pm_prepare(j, K, L, T, steps, &nsteps));
-    if (j->slab || nsteps == 0 || nplanes < 2) {  // nothing to overlap (or halo exchanges in the way): the plain sequence
+    if ((j->slab && !j->p2p && j->ctx->nranks > 1) || nsteps == 0 || nplanes < 2) {  // nothing to overlap: the plain sequence
         TRY(job_upload_image(j, planes));
         return nsteps ? job_perona_malik(j, K, L, T, nullptr) : CVB_OK;
     }
@@ -872,6 +876,7 @@ static cvb_status job_upload_image_smooth(Job *j, const uint8_t *const *planes, 
         CU(c, cudaStreamWaitEvent(c->stream, c->copy_ev[k], 0));
         CU(c, launch_replicate_halo(j->d_img + (size_t)p0 * g.plane_elems, (size_t)g.plane_elems, (size_t)g.pitch, p1 - p0, rows,
                                     g.row_lo == 0, g.row_hi == g.h, c->stream));
+        TRY(exchange_halo(j, j->d_img + (size_t)p0 * g.plane_elems, 1, p1 - p0));  // row slabs: the first step reads halo rows
         TRY(pm_run_planes(j, p0, p1 - p0, K, L, nsteps));
     }
     CU(c, cudaEventRecord(c->ev[1], c->stream));

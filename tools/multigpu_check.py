@@ -42,6 +42,10 @@ def main():
         s.init_checkerboard()
         n_pm = s.perona_malik(20.0, 0.25, 1.5)
         pm = s.download_image()
+        # the overlapped upload + PM path must give the same planes
+        n_pm2 = s.upload_image_smooth(img, 20.0, 0.25, 1.5)
+        pm2 = s.download_image()
+        assert n_pm2 == n_pm and all(np.array_equal(a, b) for a, b in zip(pm, pm2)), "upload_image_smooth differs on rank %d" % rank
         steps, norm = s.csv_run(prm, tol=0.0, max_steps=args.csv_steps)
         u = s.download_levelset()
         # and an early-stopping run: every rank must stop at the same step
