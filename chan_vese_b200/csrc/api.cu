@@ -508,17 +508,19 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
         }
     }
     const size_t pe = (size_t)g.plane_elems;
-    CU(c, cudaMalloc(&j->d_img, (size_t)count * n * pe));
-    CU(c, cudaMalloc(&j->d_u[0], (size_t)count * pe * esz(j)));
-    CU(c, cudaMalloc(&j->d_u[1], (size_t)count * pe * esz(j)));
+    // TAIL_ROWS rows of slack after the last plane: the CSV row loop fetches and prefetches past the end of its segment
+    const size_t tail = (size_t)TAIL_ROWS * g.pitch;
+    CU(c, cudaMalloc(&j->d_img, (size_t)count * n * pe + tail));
+    CU(c, cudaMalloc(&j->d_u[0], ((size_t)count * pe + tail) * esz(j)));
+    CU(c, cudaMalloc(&j->d_u[1], ((size_t)count * pe + tail) * esz(j)));
     CU(c, cudaMalloc(&j->d_state, (size_t)count * sizeof(CsvState)));
     const size_t npart = (size_t)count * g.nseg * g.ncb_csv * WARPS_PER_CTA * NACC;
     CU(c, cudaMalloc(&j->d_partials, npart * sizeof(double)));
     CU(c, cudaMalloc(&j->d_group, 2 * (size_t)NGROUPS * count * NACC * sizeof(double)));
     CU(c, cudaMallocHost(&j->h_state, 2 * (size_t)count * sizeof(CsvState)));
-    CU(c, cudaMemsetAsync(j->d_img, 0, (size_t)count * n * pe, c->stream));
-    CU(c, cudaMemsetAsync(j->d_u[0], 0, (size_t)count * pe * esz(j), c->stream));
-    CU(c, cudaMemsetAsync(j->d_u[1], 0, (size_t)count * pe * esz(j), c->stream));
+    CU(c, cudaMemsetAsync(j->d_img, 0, (size_t)count * n * pe + tail, c->stream));
+    CU(c, cudaMemsetAsync(j->d_u[0], 0, ((size_t)count * pe + tail) * esz(j), c->stream));
+    CU(c, cudaMemsetAsync(j->d_u[1], 0, ((size_t)count * pe + tail) * esz(j), c->stream));
     CU(c, cudaMemsetAsync(j->d_state, 0, (size_t)count * sizeof(CsvState), c->stream));
     CU(c, cudaMemsetAsync(j->d_partials, 0, npart * sizeof(double), c->stream));
     CU(c, cudaMemsetAsync(j->d_group, 0, 2 * (size_t)NGROUPS * count * NACC * sizeof(double), c->stream));

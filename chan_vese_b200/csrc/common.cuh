@@ -15,6 +15,8 @@
 namespace cvb {
 
 constexpr int HALO = 2;            // halo rows above and below a slab (PM needs 2/2, CSV 2/1)
+constexpr int TAIL_ROWS = 12;      // rows of slack after the last plane of the u / image buffers (CSV register + L2 prefetch
+                                   // run unconditionally up to CSV_PF + 1 rows past the end of a segment)
 constexpr int WARPS_PER_CTA = 1;   // a CTA = one warp = one column strip of one row segment: no block barriers,
                                    // a finished warp frees its slot immediately (up to 32 resident CTAs per SM)
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;

@@ -116,7 +116,7 @@ struct StepCoef {
 template <int NCH, bool EDGE>
 __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, double *__restrict__ uout,
                                               const uint8_t *__restrict__ im, const Geom &G, const StepCoef<NCH> &K,
-                                              const double *s_tab, int ra, int rb, int a, int lane, double (&acc)[NACC]) {
+                                              const double2 *s_tab, int ra, int rb, int a, int lane, double (&acc)[NACC]) {
     const int w = G.w;
     const bool colok = !EDGE || (a >= 0 && a < G.pitch);
     const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
@@ -296,10 +296,420 @@ __device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, do
     }
 }
 
+
+// ---- fast path, lean version ---------------------------------------------------------------------------
+// The same arithmetic as csv_rows_fast, arranged for the instruction-issue budget (profiles/README.md: a sub-partition
+// spends ~2 cycles per FP64 instruction PLUS ~1.2 per integer/move instruction and ~4 per LDG/SHFL/MUFU):
+//   * no branches in the row loop: the register prefetch (rows i+2, i+3 of u; i+1, i+2 of the image) and the L2
+//     prefetch run unconditionally, past the end of the segment if need be -- the rows exist (halo rows, the next
+//     plane, or the allocation's tail padding, see CSV_TAIL_ROWS in api.cu) and their values are never used;
+//   * the four row slots (C, S, q0, q1) rotate with period 4 = the unroll factor, so the rotation costs no moves;
+//   * one running 16-byte index (row * pitch + a) / 2 addresses every plane: one IMAD.WIDE per access;
+//   * one L2-prefetch instruction per row: lanes 0-16 cover the sectors of the u row strip further down, lanes
+//     17.. the sectors of the image row strips;
+//   * LINEAR (lambda1 == lambda2) is a template parameter; the atan table holds {atan(c)/pi, c} pairs.
+template <int NCH, bool EDGE, bool LINEAR>
+__device__ __forceinline__ void csv_rows_lean(const double *__restrict__ uin, double *__restrict__ uout,
+                                              const uint8_t *__restrict__ im, const Geom &G, const StepCoef<NCH> &K,
+                                              const double2 *s_tab, int ra, int rb, int a, int lane, double (&acc)[NACC]) {
+    const int w = G.w;
+    const bool colok = !EDGE || (a >= 0 && a < G.pitch);
+    const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
+    const bool v0 = lane >= 1 && (!EDGE || a < w), v1 = lane >= 1 && (!EDGE || a + 1 < w);
+    const bool l31 = lane == 31 && (!EDGE || a + 2 < G.pitch);
+    const unsigned int p2 = (unsigned int)G.pitch >> 1;  // row pitch in 16-byte (u) / 2-byte (image) units
+    const size_t pe = (size_t)G.plane_elems;
+    // index of (row ra, column a); bases are shifted so that the same index addresses the rows being fetched
+    unsigned int o = (unsigned int)(ra - G.row_lo + HALO) * p2 + (unsigned int)(a >> 1);
+    const double2 *bu = reinterpret_cast<const double2 *>(uin);   // row i
+    double2 *bo = reinterpret_cast<double2 *>(uout);              // row i
+    const double2 *bu3 = bu + 3 * (size_t)p2;                     // row i + 3
+    const unsigned short *bi[NCH];                                // row i + 2
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) bi[c] = reinterpret_cast<const unsigned short *>(im + c * pe) + 2 * (size_t)p2;
+    auto ld2 = [&](const double2 *p) { return colok ? __ldg(p) : make_double2(0.0, 0.0); };
+    auto ldi = [&](const unsigned short *p) -> unsigned int { return colok ? (unsigned int)__ldg(p) : 0u; };
+    auto lde = [&](const double2 *p) { return l31 ? __ldg(reinterpret_cast<const double *>(p + 1)) : 0.0; };
+
+    // prime: rows ra-2, ra-1, ra
+    const double2 R0 = ld2(bu + o - 2 * p2);
+    const double2 R1 = ld2(bu + o - p2);
+    double2 C = ld2(bu + o);
+    double e2c = lde(bu + o);
+    double dN0 = C.x - R1.x, dN1 = C.y - R1.y;
+    double nyp0 = normal_component<false>(dN0, dN0 + (R1.x - R0.x));
+    double nyp1 = normal_component<false>(dN1, dN1 + (R1.y - R0.y));
+    // register prefetch: rows ra+1, ra+2 of u, rows ra, ra+1 of the image
+    double2 q0 = ld2(bu + o + p2), q1 = ld2(bu + o + 2 * p2);
+    double f0 = lde(bu + o + p2), f1 = lde(bu + o + 2 * p2);
+    if (ra == 0) {
+        // image top: the halo rows hold copies of row 0 (BORDER_REPLICATE), so dN = 0; the y-term of kappa must vanish
+        // in row 0 (ny(-1) := ny(0), src/main.cpp:372): start from the very value the loop will compute for ny(0)
+        nyp0 = normal_component<false>(q0.x - C.x, (q0.x - C.x) + dN0);
+        nyp1 = normal_component<false>(q0.y - C.y, (q0.y - C.y) + dN1);
+    }
+    unsigned int j0[NCH], j1[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        j0[c] = ldi(bi[c] + o - 2 * p2);
+        j1[c] = ldi(bi[c] + o - p2);
+    }
+    // L2 prefetch, one instruction per row: lane l < 17 takes sector l of the u row strip (512 bytes from a 16-byte
+    // aligned address) CSV_PF - 2 rows ahead of the row being fetched into registers, lanes 17 .. 17+3*NCH-1 the (up to
+    // three) sectors of the image row strips
+    // address = pbase + o * pscale (one IMAD.WIDE per row), o = the running row index of the loop
+    const char *pbase = reinterpret_cast<const char *>(bu3 + (size_t)(CSV_PF - 2) * p2) + 16 * lane;
+    unsigned int pscale = 16;
+    bool pf_on = CSV_PF > 0 && lane < 17;
+    if (lane >= 17) {
+        const int k = lane - 17, c = k / 3;
+        pf_on = CSV_PF > 0 && k < 3 * NCH;
+        pbase = reinterpret_cast<const char *>(bi[c < NCH ? c : 0] + (size_t)(CSV_PF - 2) * p2) - 2 * lane + 32 * (k % 3);
+        pscale = 2;
+    }
+    if (EDGE) pf_on = false;
+
+    double accA = 0.0, accS = 0.0, accI[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) accI[c] = 0.0;
+    const int n = rb - ra;
+
+#pragma unroll 4
+    for (int r = 0; r < n; ++r) {
+        const double2 S = q0;
+        const double e2s = f0;
+        unsigned int Ib[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) Ib[c] = j0[c];
+        q0 = q1;
+        f0 = f1;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) j0[c] = j1[c];
+        // rows i+3 of u and i+2 of the image (past the segment end their values are never used)
+        q1 = ld2(bu3 + o);
+        f1 = lde(bu3 + o);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) j1[c] = ldi(bi[c] + o);
+        if (pf_on) prefetch_l2(pbase + (size_t)o * pscale);
+
+        // curvature (:342-375)
+        const double upy0 = S.x - C.x, upy1 = S.y - C.y;
+        const double ny0 = normal_component<false>(upy0, upy0 + dN0);
+        const double ny1 = normal_component<false>(upy1, upy1 + dN1);
+        double Wn = __shfl_up_sync(0xffffffffu, C.y, 1);
+        double E2 = __shfl_down_sync(0xffffffffu, C.x, 1);
+        E2 = (lane == 31) ? e2c : E2;
+        double E0 = C.y;
+        if (EDGE) {
+            Wn = first ? C.x : Wn;
+            E0 = last0 ? C.x : C.y;
+            E2 = last1 ? C.y : E2;
+        }
+        const double nx0 = normal_component<false>(E0 - C.x, E0 - Wn);
+        const double nx1 = normal_component<false>(E2 - C.y, E2 - C.x);
+        const double nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
+        double kx0 = nx0 - nxw;
+        if (EDGE) kx0 = first ? 0.0 : kx0;
+        const double kap0 = kx0 + (ny0 - nyp0);
+        const double kap1 = (nx1 - nx0) + (ny1 - nyp1);
+        // data term + combine (:968-985), delta (:988-992), update (:994)
+        double I0[NCH], I1[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            I0[c] = u8_to_double(Ib[c] & 0xffu);
+            I1[c] = u8_to_double(Ib[c] >> 8);
+        }
+        double t0 = K.q0, t1 = K.q0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            if (LINEAR) {
+                t0 = fma(K.cB[c], I0[c], t0);
+                t1 = fma(K.cB[c], I1[c], t1);
+            } else {
+                t0 = fma(fma(K.cA[c], I0[c], K.cB[c]), I0[c], t0);
+                t1 = fma(fma(K.cA[c], I1[c], K.cB[c]), I1[c], t1);
+            }
+        }
+        t0 = fma(kap0, K.alphap, t0);
+        t1 = fma(kap1, K.alphap, t1);
+        // one reciprocal for both pixels: 1/s0 = s1/(s0*s1), 1/s1 = s0/(s0*s1)
+        const double s0 = fma(C.x, C.x, K.eps2), s1 = fma(C.y, C.y, K.eps2);
+        const double rs = fast_rcp(s0 * s1);
+        const double du0 = t0 * (rs * s1);
+        const double du1 = t1 * (rs * s0);
+        const double un0 = C.x + du0, un1 = C.y + du1;
+        if (EDGE) {
+            if (v1)
+                bo[o] = make_double2(un0, un1);
+            else if (v0)
+                *reinterpret_cast<double *>(bo + o) = un0;
+        } else if (lane) {
+            bo[o] = make_double2(un0, un1);
+        }
+        o += p2;
+
+        // sums of the updated level set and of du^2 (lane 0 is a halo lane: its sums are dropped at the end)
+        double a0, a1;
+        atan_over_pi2(un0 * K.inv_eps, un1 * K.inv_eps, s_tab, a0, a1);
+        double dq0 = du0, dq1 = du1;
+        if (EDGE) {  // columns beyond the image do not count
+            a0 = v0 ? a0 : 0.0;
+            a1 = v1 ? a1 : 0.0;
+            dq0 = v0 ? du0 : 0.0;
+            dq1 = v1 ? du1 : 0.0;
+        }
+        accA += a0;
+        accA += a1;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            accI[c] = fma(I0[c], a0, accI[c]);
+            accI[c] = fma(I1[c], a1, accI[c]);
+        }
+        accS = fma(dq0, dq0, accS);
+        accS = fma(dq1, dq1, accS);
+        // next row
+        dN0 = upy0;
+        dN1 = upy1;
+        nyp0 = ny0;
+        nyp1 = ny1;
+        C = S;
+        e2c = e2s;
+    }
+    if (lane) {
+        acc[ACC_A] = accA;
+        acc[ACC_SQ] = accS;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = accI[c];
+    }
+}
+
+
+// ---- fast path with an asynchronous shared-memory row ring ---------------------------------------------
+// Rows travel HBM -> shared memory with cp.async (LDGSTS, 16-byte chunks, L2-only) RING_NS - 1 rows ahead of the row
+// being computed: no registers are held by data in flight (ptxas sank the register prefetch of the earlier versions
+// next to its first use to stay within 128 registers, profiles/README.md r1e), the prefetch distance is deep enough for
+// the HBM latency-bandwidth product (7 rows x 0.8 KB x 16 warps per SM), and the east / west neighbours are read from
+// the ring instead of being shuffled.
+// Slot of row k (k = i - ra; RING_SLOT bytes at (k % RING_NS) * RING_SLOT):
+//   [16 + 16*j, +16)          chunk j = 0..32 of the u row: columns cs-2+2j, cs-1+2j (lane j's two columns; chunk 32
+//                             holds lane 31's east neighbour)
+//   [RING_IMG + 80*c, +80)    image row of channel c from the 16-byte aligned column (cs-2) & ~15
+// Per row: two LDGSTS warp-instructions (lanes 0..31: u chunks 0..31; lanes 0..5*NCH-1: image chunks, lane 15+: u
+// chunk 32), one commit, one wait.  Rows past the end of the segment are fetched too and never used (TAIL_ROWS).
+// With RING_NS = 8 and the loop unrolled 4x the slot offsets are compile-time constants on top of one toggling base.
+constexpr int RING_NS = 8;
+constexpr int RING_SLOT = 1024;
+constexpr int RING_U = 16;
+constexpr int RING_IMG = RING_U + 33 * 16;
+constexpr int RING_BYTES = RING_NS * RING_SLOT;
+static_assert(RING_IMG + 80 * MAX_CH <= RING_SLOT, "slot too small");
+static_assert(RING_NS - 1 <= TAIL_ROWS, "tail padding too small for the ring");
+
+__device__ __forceinline__ void cp_async16(unsigned int dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int NCH, bool EDGE, bool LINEAR>
+__device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, double *__restrict__ uout,
+                                              const uint8_t *__restrict__ im, const Geom &G, const StepCoef<NCH> &K,
+                                              const double2 *s_tab, unsigned char *ring, int ra, int rb, int cs, int lane,
+                                              double (&acc)[NACC]) {
+    const int w = G.w;
+    const int a = cs - 2 + 2 * lane;
+    const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
+    const bool v0 = lane >= 1 && (!EDGE || a < w), v1 = lane >= 1 && (!EDGE || a + 1 < w);
+    const unsigned int p2 = (unsigned int)G.pitch >> 1;  // row pitch in 16-byte (u) / 2-byte (image) units
+    const size_t pe = (size_t)G.plane_elems;
+    // 16-byte index of (row ra, column a) in a u plane; 2 * o = byte index of the same position in an image plane
+    unsigned int o = (unsigned int)(ra - G.row_lo + HALO) * p2 + (unsigned int)(a >> 1);
+    const double2 *bu = reinterpret_cast<const double2 *>(uin);
+    double2 *bo = reinterpret_cast<double2 *>(uout);
+
+    // ---- the two copy instructions of a row: per-lane source = base + o * scale, per-lane slot offset
+    const int s_al = (cs - 2) & ~15;            // first column of the image chunks
+    const int dsh = (cs - 2) - s_al;            // byte offset of column cs-2 inside the image strip
+    const bool ok1 = !EDGE || (a >= 0 && a < G.pitch);
+    const unsigned int dst1 = RING_U + 16 * lane;
+    const char *base2 = reinterpret_cast<const char *>(uin) + 16 * (32 - lane);  // u chunk 32 (lanes >= 5*NCH)
+    unsigned int scale2 = 16, dst2 = RING_U + 16 * 32;
+    bool ok2 = lane == 15 && (!EDGE || a + 2 * (32 - lane) < G.pitch);
+    if (lane < 5 * NCH) {
+        const int c = lane / 5, q = lane % 5, col = s_al + 16 * q;
+        base2 = reinterpret_cast<const char *>(im) + (size_t)c * pe + (col - a);
+        scale2 = 2;
+        dst2 = RING_IMG + 80 * c + 16 * q;
+        ok2 = !EDGE || (col >= 0 && col < G.pitch);
+    }
+    const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring);
+    auto issue = [&](unsigned int orow, unsigned int slot_off) {  // orow: index of (row, column a)
+        if (ok1) cp_async16(ring_s + slot_off + dst1, bu + orow);
+        if (ok2) cp_async16(ring_s + slot_off + dst2, base2 + (size_t)orow * scale2);
+        cp_async_commit();
+    };
+    // prologue: rows ra .. ra+NS-2 into slots 0 .. NS-2
+#pragma unroll
+    for (int k = 0; k < RING_NS - 1; ++k) issue(o + k * p2, k * RING_SLOT);
+
+    // rows ra-2, ra-1 (own columns only) straight from global memory
+    const double2 R0 = ok1 ? __ldg(bu + o - 2 * p2) : make_double2(0.0, 0.0);
+    const double2 R1 = ok1 ? __ldg(bu + o - p2) : make_double2(0.0, 0.0);
+    const unsigned char *my16 = ring + 16 * lane;        // + slot: own chunk is at RING_U, west at RING_U - 8, east + 16
+    const unsigned char *my2 = ring + dsh + 2 * lane;    // + slot + RING_IMG + 80 c: own two image bytes
+    cp_async_wait<RING_NS - 3>();  // rows ra and ra+1 have landed
+    __syncwarp();
+    double2 C = *reinterpret_cast<const double2 *>(my16 + RING_U);
+    double CW = *reinterpret_cast<const double *>(my16 + RING_U - 8);
+    double CE = *reinterpret_cast<const double *>(my16 + RING_U + 16);
+    double dN0 = C.x - R1.x, dN1 = C.y - R1.y;
+    double nyp0 = normal_component<false>(dN0, dN0 + (R1.x - R0.x));
+    double nyp1 = normal_component<false>(dN1, dN1 + (R1.y - R0.y));
+    if (ra == 0) {
+        // image top: the halo rows hold copies of row 0 (BORDER_REPLICATE), so dN = 0; the y-term of kappa must vanish
+        // in row 0 (ny(-1) := ny(0), src/main.cpp:372): start from the very value the loop will compute for ny(0)
+        const double2 q = *reinterpret_cast<const double2 *>(my16 + RING_SLOT + RING_U);
+        nyp0 = normal_component<false>(q.x - C.x, (q.x - C.x) + dN0);
+        nyp1 = normal_component<false>(q.y - C.y, (q.y - C.y) + dN1);
+    }
+
+    double accA = 0.0, accS = 0.0, accI[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) accI[c] = 0.0;
+    const int n = rb - ra;
+    o += (RING_NS - 1) * p2;  // the row being fetched; the row being computed is RING_NS - 1 rows behind
+    const double2 *bo_c = bo - (size_t)(RING_NS - 1) * p2;
+
+    // one row: s_wr = slot of row i-1 (free, receives row i+NS-1), s_img = slot of row i, s_u = slot of row i+1
+    auto row = [&](unsigned int s_wr, unsigned int s_img, unsigned int s_u) {
+        issue(o, s_wr);
+        cp_async_wait<RING_NS - 2>();  // row i+1 has landed
+        __syncwarp();
+        const double2 S = *reinterpret_cast<const double2 *>(my16 + s_u + RING_U);
+        const double SW = *reinterpret_cast<const double *>(my16 + s_u + RING_U - 8);
+        const double SE = *reinterpret_cast<const double *>(my16 + s_u + RING_U + 16);
+        unsigned int Ib[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) Ib[c] = *reinterpret_cast<const unsigned short *>(my2 + s_img + RING_IMG + 80 * c);
+
+        // curvature (:342-375)
+        const double upy0 = S.x - C.x, upy1 = S.y - C.y;
+        const double ny0 = normal_component<false>(upy0, upy0 + dN0);
+        const double ny1 = normal_component<false>(upy1, upy1 + dN1);
+        double Wn = CW, E2 = CE, E0 = C.y;
+        if (EDGE) {
+            Wn = first ? C.x : Wn;
+            E0 = last0 ? C.x : C.y;
+            E2 = last1 ? C.y : E2;
+        }
+        const double nx0 = normal_component<false>(E0 - C.x, E0 - Wn);
+        const double nx1 = normal_component<false>(E2 - C.y, E2 - C.x);
+        const double nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
+        double kx0 = nx0 - nxw;
+        if (EDGE) kx0 = first ? 0.0 : kx0;
+        const double kap0 = kx0 + (ny0 - nyp0);
+        const double kap1 = (nx1 - nx0) + (ny1 - nyp1);
+        // data term + combine (:968-985), delta (:988-992), update (:994)
+        double I0[NCH], I1[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            I0[c] = u8_to_double(Ib[c] & 0xffu);
+            I1[c] = u8_to_double(Ib[c] >> 8);
+        }
+        double t0 = K.q0, t1 = K.q0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            if (LINEAR) {
+                t0 = fma(K.cB[c], I0[c], t0);
+                t1 = fma(K.cB[c], I1[c], t1);
+            } else {
+                t0 = fma(fma(K.cA[c], I0[c], K.cB[c]), I0[c], t0);
+                t1 = fma(fma(K.cA[c], I1[c], K.cB[c]), I1[c], t1);
+            }
+        }
+        t0 = fma(kap0, K.alphap, t0);
+        t1 = fma(kap1, K.alphap, t1);
+        // one reciprocal for both pixels: 1/s0 = s1/(s0*s1), 1/s1 = s0/(s0*s1)
+        const double s0 = fma(C.x, C.x, K.eps2), s1 = fma(C.y, C.y, K.eps2);
+        const double rs = fast_rcp(s0 * s1);
+        const double du0 = t0 * (rs * s1);
+        const double du1 = t1 * (rs * s0);
+        const double un0 = C.x + du0, un1 = C.y + du1;
+        double2 *po = const_cast<double2 *>(bo_c) + o;
+        if (EDGE) {
+            if (v1)
+                *po = make_double2(un0, un1);
+            else if (v0)
+                *reinterpret_cast<double *>(po) = un0;
+        } else if (lane) {
+            *po = make_double2(un0, un1);
+        }
+        o += p2;
+
+        // sums of the updated level set and of du^2 (lane 0 is a halo lane: its sums are dropped at the end)
+        double a0, a1;
+        atan_over_pi2(un0 * K.inv_eps, un1 * K.inv_eps, s_tab, a0, a1);
+        double dq0 = du0, dq1 = du1;
+        if (EDGE) {  // columns beyond the image do not count
+            a0 = v0 ? a0 : 0.0;
+            a1 = v1 ? a1 : 0.0;
+            dq0 = v0 ? du0 : 0.0;
+            dq1 = v1 ? du1 : 0.0;
+        }
+        accA += a0;
+        accA += a1;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            accI[c] = fma(I0[c], a0, accI[c]);
+            accI[c] = fma(I1[c], a1, accI[c]);
+        }
+        accS = fma(dq0, dq0, accS);
+        accS = fma(dq1, dq1, accS);
+        // next row
+        dN0 = upy0;
+        dN1 = upy1;
+        nyp0 = ny0;
+        nyp1 = ny1;
+        C = S;
+        CW = SW;
+        CE = SE;
+    };
+
+    int r = 0;
+    unsigned int tog = 0;  // offset of slot 0 or slot 4: the slot of the first row of a group of four
+#pragma unroll 1
+    for (; r + 4 <= n; r += 4) {
+        const unsigned int t2 = tog ^ (4 * RING_SLOT);
+        row(t2 + 3 * RING_SLOT, tog, tog + RING_SLOT);
+        row(tog, tog + RING_SLOT, tog + 2 * RING_SLOT);
+        row(tog + RING_SLOT, tog + 2 * RING_SLOT, tog + 3 * RING_SLOT);
+        row(tog + 2 * RING_SLOT, tog + 3 * RING_SLOT, t2);
+        tog = t2;
+    }
+#pragma unroll 1
+    for (; r < n; ++r) {
+        const unsigned int k = (unsigned int)r;
+        row(((k + RING_NS - 1) % RING_NS) * RING_SLOT, (k % RING_NS) * RING_SLOT, ((k + 1) % RING_NS) * RING_SLOT);
+    }
+    cp_async_wait<0>();  // nothing may land in the ring after the CTA has gone
+    if (lane) {
+        acc[ACC_A] = accA;
+        acc[ACC_SQ] = accS;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = accI[c];
+    }
+}
+
 template <int NCH, bool STRICT, int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(const __grid_constant__ CsvArgs A) {
     const Geom &G = A.g;
-    __shared__ double s_tab[ATAN_TAB_N];
+    __shared__ double2 s_tab[ATAN_TAB_N];  // {atan(c_q)/pi, c_q}
+#if !defined(CSV_OLD_FAST) && !defined(CSV_LEAN)
+    __shared__ __align__(16) unsigned char s_ring[(MODE == MODE_STEP && !STRICT) ? RING_BYTES : 16];
+#endif
     const int lane = threadIdx.x;
     constexpr int warp = 0;
     int bid = blockIdx.x;
@@ -309,7 +719,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     const int img = bid / G.nseg;
     CsvState *st = A.state + img;
 #pragma unroll
-    for (int q = 0; q < ATAN_TAB_N; q += 32) s_tab[q + lane] = A.atan_tab[q + lane];
+    for (int q = 0; q < ATAN_TAB_N; q += 32) s_tab[q + lane] = make_double2(A.atan_tab[q + lane], atan_centre(q + lane));
 #ifndef CSV_NO_PDL
     if (MODE == MODE_STEP && !STRICT) {
         // launched with programmatic stream serialization: everything above is independent of the previous launch;
@@ -387,11 +797,37 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     // (image top and bottom included: the halo rows there hold copies of the border rows, see replicate_border_rows)
     const bool interior = !STRICT && MODE == MODE_STEP && cb > 0 && (cb + 1) * CSV_CB < w;
     const bool edge_fast = !STRICT && MODE == MODE_STEP && !interior && cs < w;
+#ifdef CSV_OLD_FAST
     if (interior) {
         csv_rows_fast<NCH, false>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
     } else if (edge_fast) {
         csv_rows_fast<NCH, true>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
     } else if (cs < w) {
+#elif !defined(CSV_LEAN)
+    if (interior) {
+        if (K.linear)
+            csv_rows_ring<NCH, false, true>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
+        else
+            csv_rows_ring<NCH, false, false>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
+    } else if (edge_fast) {
+        if (K.linear)
+            csv_rows_ring<NCH, true, true>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
+        else
+            csv_rows_ring<NCH, true, false>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
+    } else if (cs < w) {
+#else
+    if (interior) {
+        if (K.linear)
+            csv_rows_lean<NCH, false, true>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
+        else
+            csv_rows_lean<NCH, false, false>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
+    } else if (edge_fast) {
+        if (K.linear)
+            csv_rows_lean<NCH, true, true>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
+        else
+            csv_rows_lean<NCH, true, false>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
+    } else if (cs < w) {
+#endif
         const int nk = rb - ra + 3;  // streamed rows ra-2 .. rb
         double2 pq[CSV_D];
         double pe[CSV_D];
@@ -738,6 +1174,11 @@ static cudaError_t launch_step_n(const CsvArgs &A, bool strict, int mode, cudaSt
             // Programmatic dependent launch: the CTAs of step n+1 may become resident while the tail of step n (last
             // wave, group reductions, multi-GPU fold) is still running; they load the atan table and then block in
             // griddepcontrol.wait until step n has completed and flushed.
+            // 16 resident one-warp CTAs x (row ring + atan table) need ~210 KB of shared memory per SM
+            static cudaError_t carve = cudaFuncSetAttribute(csv_step_kernel<NCH, false, MODE_STEP>,
+                                                            cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                            (int)cudaSharedmemCarveoutMaxShared);
+            if (carve != cudaSuccess) return carve;
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
             cfg.gridDim = dim3(grid);

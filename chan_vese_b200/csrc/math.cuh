@@ -73,6 +73,20 @@ __device__ __forceinline__ void atan_reduce(double x, const double *tab, int &hx
     num = t - c;
     den = fma(t, c, 1.0);
 }
+// the same against a table of {atan(c_q)/pi, c_q} pairs (one LDS.128, no integer construction of c) and with |x|
+// as an operand modifier of the two FP64 instructions
+__device__ __forceinline__ void atan_reduce(double x, const double2 *tab, int &hx, double &num, double &den, double &hi) {
+    hx = __double2hiint(x);
+    const int hc = min(max(hx & 0x7fffffff, ATAN_HC_MIN), ATAN_HC_MAX);
+    const double2 e = tab[(hc >> 18) - ATAN_Q0];
+    const double t = fabs(x);
+    hi = e.x;
+    num = t - e.y;
+    den = fma(t, e.y, 1.0);
+}
+__device__ __forceinline__ double atan_centre(int q) {  // c_q, q = 0..ATAN_NQ-1
+    return __hiloint2double(((ATAN_Q0 + q) << 18) | 0x00020000, 0);
+}
 __device__ __forceinline__ double atan_finish(double z, double hi, int hx) {
     const double w = z * z;
     // (atan z / z - 1) / w on w in [0, 0.0704^2]: degree-4 least-squares fit on Chebyshev nodes, max error 4.4e-16
@@ -86,14 +100,16 @@ __device__ __forceinline__ double atan_finish(double z, double hi, int hx) {
     const double r = fma(at, CVB_INV_PI, hi);  // atan(t)/pi
     return __hiloint2double(__double2hiint(r) ^ (hx & 0x80000000), __double2loint(r));
 }
-__device__ __forceinline__ double atan_over_pi(double x, const double *tab /* shared memory */) {
+template <typename TAB>
+__device__ __forceinline__ double atan_over_pi(double x, const TAB *tab /* shared memory */) {
     int hx;
     double num, den, hi;
     atan_reduce(x, tab, hx, num, den, hi);
     return atan_finish(num * fast_rcp(den), hi, hx);
 }
 // two arguments sharing ONE reciprocal: 1/d0 = d1/(d0*d1), 1/d1 = d0/(d0*d1)  (d in [1, 2^90): no overflow)
-__device__ __forceinline__ void atan_over_pi2(double x0, double x1, const double *tab, double &a0, double &a1) {
+template <typename TAB>
+__device__ __forceinline__ void atan_over_pi2(double x0, double x1, const TAB *tab, double &a0, double &a1) {
     int hx0, hx1;
     double n0, d0, h0, n1, d1, h1;
     atan_reduce(x0, tab, hx0, n0, d0, h0);
