@@ -7,11 +7,12 @@
 // :973-974) of the updated level set.  Algorithmic traffic: read u 8 B + write u 8 B + N bytes of image
 // per pixel per step (the reference moves ~0.9 kB).
 //
-// Mapping: a warp marches down a strip of 64 columns, each lane owning two adjacent columns (one 16-byte
-// access); rows i-1, i, i+1 live in registers, west/east neighbours come from warp shuffles, ny(i-1)
-// is carried from the previous row.  Lane 0 is a halo lane (it supplies nx of the column left of the
-// strip), so a strip owns 62 columns and a 4-warp CTA 248.  Loads run a software pipeline: L2 prefetch
-// CSV_PF rows ahead, register prefetch CSV_D rows ahead.
+// Mapping: a warp (= one CTA) marches down a strip of 64 columns, each lane owning two adjacent columns; ny(i-1)
+// and u(i) - u(i-1) are carried in registers from the previous row.  Lane 0 is a halo lane (it supplies nx of the
+// column left of the strip), so a strip owns 62 columns.  Production path (csv_rows_ring): rows stream
+// HBM -> shared memory through a cp.async ring 7 rows ahead of the row being computed, east / west neighbours are
+// read from the ring.  Generic path (strict math, curvature-only mode): explicit clamps, register prefetch CSV_D rows
+// ahead and L2 prefetch CSV_PF rows ahead.
 #include <string.h>
 
 #include "common.cuh"
@@ -20,11 +21,6 @@
 #include "reduce.cuh"
 
 namespace cvb {
-
-#ifndef CSV_UNROLL
-#define CSV_UNROLL 2
-#endif
-constexpr int kCsvUnroll = CSV_UNROLL;  // unroll factor of the fast-path row loop
 
 #ifndef CSV_D
 #define CSV_D 2
@@ -104,385 +100,6 @@ struct StepCoef {
     double eps2, inv_eps;
     bool linear;              // all A_k == 0 (lambda1 == lambda2, the reference's default): the data term is linear in I
 };
-
-// ---- interior fast path ---------------------------------------------------------------------------------
-// For CTAs whose stencils never touch an image border (all but the outermost ring of CTAs): no clamping,
-// no border selects, no validity masks; the row recurrence carries u(i) - u(i-1) instead of row i-1, so
-// only two row ages are live and a 2x unrolled loop needs no register moves.  One output row per iteration:
-//   in:  C = u(i,.), dN = u(i,.) - u(i-1,.), nyp = ny(i-1,.), S = u(i+1,.)
-// EDGE: the strip touches the left or right image border (BORDER_REPLICATE in j, :351,353, and on the normalised
-// field, :371): loads are predicated, the first column has no west neighbour and a zero x-term, the last column no
-// east neighbour, columns beyond w are neither stored nor summed.  Interior strips compile all of that away.
-template <int NCH, bool EDGE>
-__device__ __forceinline__ void csv_rows_fast(const double *__restrict__ uin, double *__restrict__ uout,
-                                              const uint8_t *__restrict__ im, const Geom &G, const StepCoef<NCH> &K,
-                                              const double2 *s_tab, int ra, int rb, int a, int lane, double (&acc)[NACC]) {
-    const int w = G.w;
-    const bool colok = !EDGE || (a >= 0 && a < G.pitch);
-    const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
-    const bool v0 = lane >= 1 && (!EDGE || a < w), v1 = lane >= 1 && (!EDGE || a + 1 < w);
-    auto ld2 = [&](const double *p) { return colok ? __ldg(reinterpret_cast<const double2 *>(p)) : make_double2(0.0, 0.0); };
-    auto ldi = [&](const uint8_t *p) -> unsigned int { return colok ? __ldg(reinterpret_cast<const unsigned short *>(p)) : 0u; };
-    const size_t pitch = (size_t)G.pitch;
-    const double *pu = uin + (size_t)(ra - 2 - G.row_lo + HALO) * pitch + a;  // row ra-2
-    double *po = uout + (size_t)(ra - G.row_lo + HALO) * pitch + a;           // row ra
-    const uint8_t *pi = im + (size_t)(ra - G.row_lo + HALO) * pitch + a;      // row ra, channel 0
-    const size_t pe = (size_t)G.plane_elems;
-    const bool l31 = lane == 31 && (!EDGE || a + 2 < G.pitch);
-
-    // prime: rows ra-2, ra-1, ra
-    const double2 R0 = ld2(pu);
-    const double2 R1 = ld2(pu + pitch);
-    double2 C = ld2(pu + 2 * pitch);
-    double e2c = l31 ? __ldg(pu + 2 * pitch + 2) : 0.0;
-    double dN0 = C.x - R1.x, dN1 = C.y - R1.y;
-    double nyp0 = normal_component<false>(dN0, dN0 + (R1.x - R0.x));
-    double nyp1 = normal_component<false>(dN1, dN1 + (R1.y - R0.y));
-    pu += 3 * pitch;  // row ra+1
-
-    // register prefetch: rows i+1 and i+2 of u, rows i and i+1 of the image
-    double2 q0 = ld2(pu), q1 = make_double2(0.0, 0.0);
-    if (ra == 0) {
-        // image top: the halo rows hold copies of row 0 (BORDER_REPLICATE), so dN = 0; the y-term of kappa must vanish
-        // in row 0 (ny(-1) := ny(0), src/main.cpp:372): start from the very value the loop will compute for ny(0)
-        nyp0 = normal_component<false>(q0.x - C.x, (q0.x - C.x) + dN0);
-        nyp1 = normal_component<false>(q0.y - C.y, (q0.y - C.y) + dN1);
-    }
-    double f0 = l31 ? __ldg(pu + 2) : 0.0, f1 = 0.0;
-    unsigned int j0[NCH], j1[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        j0[c] = ldi(pi + c * pe);
-        j1[c] = 0u;
-    }
-    const int n = rb - ra;
-    if (n > 1) {
-        q1 = ld2(pu + pitch);
-        if (l31) f1 = __ldg(pu + pitch + 2);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) j1[c] = ldi(pi + pitch + c * pe);
-    }
-    pu += 2 * pitch;  // row ra+3: next row to fetch
-    pi += 2 * pitch;  // row ra+2
-
-    double accA = 0.0, accS = 0.0, accI[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) accI[c] = 0.0;
-
-#pragma unroll kCsvUnroll
-    for (int r = 0; r < n; ++r) {
-        const double2 S = q0;
-        const double e2s = f0;
-        unsigned int Ib[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) Ib[c] = j0[c];
-#ifdef CSV_FAST_D1
-        if (r + 1 < n) {  // one row ahead only: rows (ra+r)+2 of u and (ra+r)+1 of the image
-            q0 = ld2(pu - pitch);
-            if (l31) f0 = __ldg(pu - pitch + 2);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) j0[c] = ldi(pi - pitch + c * pe);
-        }
-#else
-        q0 = q1;
-        f0 = f1;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) j0[c] = j1[c];
-        if (r + 2 < n) {  // rows (ra+r)+3 of u and (ra+r)+2 of the image
-            q1 = ld2(pu);
-            if (l31) f1 = __ldg(pu + 2);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) j1[c] = ldi(pi + c * pe);
-        }
-#endif
-        if (CSV_PF > 0 && r + CSV_PF < n) {
-            prefetch_l2(pu + (size_t)(CSV_PF - 2) * pitch);
-            if (lane < 3 * NCH) prefetch_l2(pi + (size_t)(CSV_PF - 2) * pitch + (lane / 3) * pe + (2 - 2 * lane + (lane % 3) * 31));
-        }
-        pu += pitch;
-        pi += pitch;
-
-        // curvature (:342-375)
-        const double upy0 = S.x - C.x, upy1 = S.y - C.y;
-        const double ny0 = normal_component<false>(upy0, upy0 + dN0);
-        const double ny1 = normal_component<false>(upy1, upy1 + dN1);
-        double Wn = __shfl_up_sync(0xffffffffu, C.y, 1);
-        double E2 = __shfl_down_sync(0xffffffffu, C.x, 1);
-        E2 = (lane == 31) ? e2c : E2;
-        double E0 = C.y;
-        if (EDGE) {
-            Wn = first ? C.x : Wn;
-            E0 = last0 ? C.x : C.y;
-            E2 = last1 ? C.y : E2;
-        }
-        const double nx0 = normal_component<false>(E0 - C.x, E0 - Wn);
-        const double nx1 = normal_component<false>(E2 - C.y, E2 - C.x);
-        const double nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
-        double kx0 = nx0 - nxw;
-        if (EDGE) kx0 = first ? 0.0 : kx0;
-        const double kap0 = kx0 + (ny0 - nyp0);
-        const double kap1 = (nx1 - nx0) + (ny1 - nyp1);
-        // data term + combine (:968-985), delta (:988-992), update (:994)
-        double I0[NCH], I1[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            I0[c] = u8_to_double(Ib[c] & 0xffu);
-            I1[c] = u8_to_double(Ib[c] >> 8);
-        }
-        double t0 = K.q0, t1 = K.q0;
-        if (K.linear) {  // warp-uniform
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                t0 = fma(K.cB[c], I0[c], t0);
-                t1 = fma(K.cB[c], I1[c], t1);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                t0 = fma(fma(K.cA[c], I0[c], K.cB[c]), I0[c], t0);
-                t1 = fma(fma(K.cA[c], I1[c], K.cB[c]), I1[c], t1);
-            }
-        }
-        t0 = fma(kap0, K.alphap, t0);
-        t1 = fma(kap1, K.alphap, t1);
-        // one reciprocal for both pixels: 1/s0 = s1/(s0*s1), 1/s1 = s0/(s0*s1)
-        const double s0 = fma(C.x, C.x, K.eps2), s1 = fma(C.y, C.y, K.eps2);
-        const double rs = fast_rcp(s0 * s1);
-        const double du0 = t0 * (rs * s1);
-        const double du1 = t1 * (rs * s0);
-        const double un0 = C.x + du0, un1 = C.y + du1;
-        if (EDGE) {
-            if (v1)
-                *reinterpret_cast<double2 *>(po) = make_double2(un0, un1);
-            else if (v0)
-                *po = un0;
-        } else if (lane) {
-            *reinterpret_cast<double2 *>(po) = make_double2(un0, un1);
-        }
-        po += pitch;
-
-        // sums of the updated level set and of du^2 (lane 0 is a halo lane: its sums are dropped at the end)
-        double a0, a1;
-        atan_over_pi2(un0 * K.inv_eps, un1 * K.inv_eps, s_tab, a0, a1);
-        double dq0 = du0, dq1 = du1;
-        if (EDGE) {  // columns beyond the image do not count
-            a0 = v0 ? a0 : 0.0;
-            a1 = v1 ? a1 : 0.0;
-            dq0 = v0 ? du0 : 0.0;
-            dq1 = v1 ? du1 : 0.0;
-        }
-        accA += a0;
-        accA += a1;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            accI[c] = fma(I0[c], a0, accI[c]);
-            accI[c] = fma(I1[c], a1, accI[c]);
-        }
-        accS = fma(dq0, dq0, accS);
-        accS = fma(dq1, dq1, accS);
-        // next row
-        dN0 = upy0;
-        dN1 = upy1;
-        nyp0 = ny0;
-        nyp1 = ny1;
-        C = S;
-        e2c = e2s;
-    }
-    if (lane) {
-        acc[ACC_A] = accA;
-        acc[ACC_SQ] = accS;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = accI[c];
-    }
-}
-
-
-// ---- fast path, lean version ---------------------------------------------------------------------------
-// The same arithmetic as csv_rows_fast, arranged for the instruction-issue budget (profiles/README.md: a sub-partition
-// spends ~2 cycles per FP64 instruction PLUS ~1.2 per integer/move instruction and ~4 per LDG/SHFL/MUFU):
-//   * no branches in the row loop: the register prefetch (rows i+2, i+3 of u; i+1, i+2 of the image) and the L2
-//     prefetch run unconditionally, past the end of the segment if need be -- the rows exist (halo rows, the next
-//     plane, or the allocation's tail padding, see CSV_TAIL_ROWS in api.cu) and their values are never used;
-//   * the four row slots (C, S, q0, q1) rotate with period 4 = the unroll factor, so the rotation costs no moves;
-//   * one running 16-byte index (row * pitch + a) / 2 addresses every plane: one IMAD.WIDE per access;
-//   * one L2-prefetch instruction per row: lanes 0-16 cover the sectors of the u row strip further down, lanes
-//     17.. the sectors of the image row strips;
-//   * LINEAR (lambda1 == lambda2) is a template parameter; the atan table holds {atan(c)/pi, c} pairs.
-template <int NCH, bool EDGE, bool LINEAR>
-__device__ __forceinline__ void csv_rows_lean(const double *__restrict__ uin, double *__restrict__ uout,
-                                              const uint8_t *__restrict__ im, const Geom &G, const StepCoef<NCH> &K,
-                                              const double2 *s_tab, int ra, int rb, int a, int lane, double (&acc)[NACC]) {
-    const int w = G.w;
-    const bool colok = !EDGE || (a >= 0 && a < G.pitch);
-    const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
-    const bool v0 = lane >= 1 && (!EDGE || a < w), v1 = lane >= 1 && (!EDGE || a + 1 < w);
-    const bool l31 = lane == 31 && (!EDGE || a + 2 < G.pitch);
-    const unsigned int p2 = (unsigned int)G.pitch >> 1;  // row pitch in 16-byte (u) / 2-byte (image) units
-    const size_t pe = (size_t)G.plane_elems;
-    // index of (row ra, column a); bases are shifted so that the same index addresses the rows being fetched
-    unsigned int o = (unsigned int)(ra - G.row_lo + HALO) * p2 + (unsigned int)(a >> 1);
-    const double2 *bu = reinterpret_cast<const double2 *>(uin);   // row i
-    double2 *bo = reinterpret_cast<double2 *>(uout);              // row i
-    const double2 *bu3 = bu + 3 * (size_t)p2;                     // row i + 3
-    const unsigned short *bi[NCH];                                // row i + 2
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) bi[c] = reinterpret_cast<const unsigned short *>(im + c * pe) + 2 * (size_t)p2;
-    auto ld2 = [&](const double2 *p) { return colok ? __ldg(p) : make_double2(0.0, 0.0); };
-    auto ldi = [&](const unsigned short *p) -> unsigned int { return colok ? (unsigned int)__ldg(p) : 0u; };
-    auto lde = [&](const double2 *p) { return l31 ? __ldg(reinterpret_cast<const double *>(p + 1)) : 0.0; };
-
-    // prime: rows ra-2, ra-1, ra
-    const double2 R0 = ld2(bu + o - 2 * p2);
-    const double2 R1 = ld2(bu + o - p2);
-    double2 C = ld2(bu + o);
-    double e2c = lde(bu + o);
-    double dN0 = C.x - R1.x, dN1 = C.y - R1.y;
-    double nyp0 = normal_component<false>(dN0, dN0 + (R1.x - R0.x));
-    double nyp1 = normal_component<false>(dN1, dN1 + (R1.y - R0.y));
-    // register prefetch: rows ra+1, ra+2 of u, rows ra, ra+1 of the image
-    double2 q0 = ld2(bu + o + p2), q1 = ld2(bu + o + 2 * p2);
-    double f0 = lde(bu + o + p2), f1 = lde(bu + o + 2 * p2);
-    if (ra == 0) {
-        // image top: the halo rows hold copies of row 0 (BORDER_REPLICATE), so dN = 0; the y-term of kappa must vanish
-        // in row 0 (ny(-1) := ny(0), src/main.cpp:372): start from the very value the loop will compute for ny(0)
-        nyp0 = normal_component<false>(q0.x - C.x, (q0.x - C.x) + dN0);
-        nyp1 = normal_component<false>(q0.y - C.y, (q0.y - C.y) + dN1);
-    }
-    unsigned int j0[NCH], j1[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        j0[c] = ldi(bi[c] + o - 2 * p2);
-        j1[c] = ldi(bi[c] + o - p2);
-    }
-    // L2 prefetch, one instruction per row: lane l < 17 takes sector l of the u row strip (512 bytes from a 16-byte
-    // aligned address) CSV_PF - 2 rows ahead of the row being fetched into registers, lanes 17 .. 17+3*NCH-1 the (up to
-    // three) sectors of the image row strips
-    // address = pbase + o * pscale (one IMAD.WIDE per row), o = the running row index of the loop
-    const char *pbase = reinterpret_cast<const char *>(bu3 + (size_t)(CSV_PF - 2) * p2) + 16 * lane;
-    unsigned int pscale = 16;
-    bool pf_on = CSV_PF > 0 && lane < 17;
-    if (lane >= 17) {
-        const int k = lane - 17, c = k / 3;
-        pf_on = CSV_PF > 0 && k < 3 * NCH;
-        pbase = reinterpret_cast<const char *>(bi[c < NCH ? c : 0] + (size_t)(CSV_PF - 2) * p2) - 2 * lane + 32 * (k % 3);
-        pscale = 2;
-    }
-    if (EDGE) pf_on = false;
-
-    double accA = 0.0, accS = 0.0, accI[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) accI[c] = 0.0;
-    const int n = rb - ra;
-
-#pragma unroll 4
-    for (int r = 0; r < n; ++r) {
-        const double2 S = q0;
-        const double e2s = f0;
-        unsigned int Ib[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) Ib[c] = j0[c];
-        q0 = q1;
-        f0 = f1;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) j0[c] = j1[c];
-        // rows i+3 of u and i+2 of the image (past the segment end their values are never used)
-        q1 = ld2(bu3 + o);
-        f1 = lde(bu3 + o);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) j1[c] = ldi(bi[c] + o);
-        if (pf_on) prefetch_l2(pbase + (size_t)o * pscale);
-
-        // curvature (:342-375)
-        const double upy0 = S.x - C.x, upy1 = S.y - C.y;
-        const double ny0 = normal_component<false>(upy0, upy0 + dN0);
-        const double ny1 = normal_component<false>(upy1, upy1 + dN1);
-        double Wn = __shfl_up_sync(0xffffffffu, C.y, 1);
-        double E2 = __shfl_down_sync(0xffffffffu, C.x, 1);
-        E2 = (lane == 31) ? e2c : E2;
-        double E0 = C.y;
-        if (EDGE) {
-            Wn = first ? C.x : Wn;
-            E0 = last0 ? C.x : C.y;
-            E2 = last1 ? C.y : E2;
-        }
-        const double nx0 = normal_component<false>(E0 - C.x, E0 - Wn);
-        const double nx1 = normal_component<false>(E2 - C.y, E2 - C.x);
-        const double nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
-        double kx0 = nx0 - nxw;
-        if (EDGE) kx0 = first ? 0.0 : kx0;
-        const double kap0 = kx0 + (ny0 - nyp0);
-        const double kap1 = (nx1 - nx0) + (ny1 - nyp1);
-        // data term + combine (:968-985), delta (:988-992), update (:994)
-        double I0[NCH], I1[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            I0[c] = u8_to_double(Ib[c] & 0xffu);
-            I1[c] = u8_to_double(Ib[c] >> 8);
-        }
-        double t0 = K.q0, t1 = K.q0;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            if (LINEAR) {
-                t0 = fma(K.cB[c], I0[c], t0);
-                t1 = fma(K.cB[c], I1[c], t1);
-            } else {
-                t0 = fma(fma(K.cA[c], I0[c], K.cB[c]), I0[c], t0);
-                t1 = fma(fma(K.cA[c], I1[c], K.cB[c]), I1[c], t1);
-            }
-        }
-        t0 = fma(kap0, K.alphap, t0);
-        t1 = fma(kap1, K.alphap, t1);
-        // one reciprocal for both pixels: 1/s0 = s1/(s0*s1), 1/s1 = s0/(s0*s1)
-        const double s0 = fma(C.x, C.x, K.eps2), s1 = fma(C.y, C.y, K.eps2);
-        const double rs = fast_rcp(s0 * s1);
-        const double du0 = t0 * (rs * s1);
-        const double du1 = t1 * (rs * s0);
-        const double un0 = C.x + du0, un1 = C.y + du1;
-        if (EDGE) {
-            if (v1)
-                bo[o] = make_double2(un0, un1);
-            else if (v0)
-                *reinterpret_cast<double *>(bo + o) = un0;
-        } else if (lane) {
-            bo[o] = make_double2(un0, un1);
-        }
-        o += p2;
-
-        // sums of the updated level set and of du^2 (lane 0 is a halo lane: its sums are dropped at the end)
-        double a0, a1;
-        atan_over_pi2(un0 * K.inv_eps, un1 * K.inv_eps, s_tab, a0, a1);
-        double dq0 = du0, dq1 = du1;
-        if (EDGE) {  // columns beyond the image do not count
-            a0 = v0 ? a0 : 0.0;
-            a1 = v1 ? a1 : 0.0;
-            dq0 = v0 ? du0 : 0.0;
-            dq1 = v1 ? du1 : 0.0;
-        }
-        accA += a0;
-        accA += a1;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            accI[c] = fma(I0[c], a0, accI[c]);
-            accI[c] = fma(I1[c], a1, accI[c]);
-        }
-        accS = fma(dq0, dq0, accS);
-        accS = fma(dq1, dq1, accS);
-        // next row
-        dN0 = upy0;
-        dN1 = upy1;
-        nyp0 = ny0;
-        nyp1 = ny1;
-        C = S;
-        e2c = e2s;
-    }
-    if (lane) {
-        acc[ACC_A] = accA;
-        acc[ACC_SQ] = accS;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = accI[c];
-    }
-}
-
 
 // ---- fast path with an asynchronous shared-memory row ring ---------------------------------------------
 // Rows travel HBM -> shared memory with cp.async (LDGSTS, 16-byte chunks, L2-only) RING_NS - 1 rows ahead of the row
@@ -707,9 +324,7 @@ template <int NCH, bool STRICT, int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(const __grid_constant__ CsvArgs A) {
     const Geom &G = A.g;
     __shared__ double2 s_tab[ATAN_TAB_N];  // {atan(c_q)/pi, c_q}
-#if !defined(CSV_OLD_FAST) && !defined(CSV_LEAN)
     __shared__ __align__(16) unsigned char s_ring[(MODE == MODE_STEP && !STRICT) ? RING_BYTES : 16];
-#endif
     const int lane = threadIdx.x;
     constexpr int warp = 0;
     int bid = blockIdx.x;
@@ -797,13 +412,6 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     // (image top and bottom included: the halo rows there hold copies of the border rows, see replicate_border_rows)
     const bool interior = !STRICT && MODE == MODE_STEP && cb > 0 && (cb + 1) * CSV_CB < w;
     const bool edge_fast = !STRICT && MODE == MODE_STEP && !interior && cs < w;
-#ifdef CSV_OLD_FAST
-    if (interior) {
-        csv_rows_fast<NCH, false>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
-    } else if (edge_fast) {
-        csv_rows_fast<NCH, true>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
-    } else if (cs < w) {
-#elif !defined(CSV_LEAN)
     if (interior) {
         if (K.linear)
             csv_rows_ring<NCH, false, true>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
@@ -815,19 +423,6 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
         else
             csv_rows_ring<NCH, true, false>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
     } else if (cs < w) {
-#else
-    if (interior) {
-        if (K.linear)
-            csv_rows_lean<NCH, false, true>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
-        else
-            csv_rows_lean<NCH, false, false>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
-    } else if (edge_fast) {
-        if (K.linear)
-            csv_rows_lean<NCH, true, true>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
-        else
-            csv_rows_lean<NCH, true, false>(uin, uout, im, G, K, s_tab, ra, rb, a, lane, acc);
-    } else if (cs < w) {
-#endif
         const int nk = rb - ra + 3;  // streamed rows ra-2 .. rb
         double2 pq[CSV_D];
         double pe[CSV_D];
