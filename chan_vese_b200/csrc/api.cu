@@ -816,7 +816,8 @@ static cvb_status pm_prepare(Job *j, double K, double L, double T, int *steps, i
     if (nsteps == 0) return CVB_OK;
     CU(c, cudaSetDevice(c->device));
     const Geom &g = j->g;
-    const size_t bytes = (size_t)g.count * g.nch * g.plane_elems * esz(j);
+    // + TAIL_ROWS rows of slack: the PM row ring requests rows past the end of its segment
+    const size_t bytes = ((size_t)g.count * g.nch * g.plane_elems + (size_t)TAIL_ROWS * g.pitch) * esz(j);
     for (int b = 0; b < (nsteps > 2 ? 2 : 1); ++b)
         if (!j->d_pm[b]) {
             CU(c, cudaMalloc(&j->d_pm[b], bytes));
@@ -1045,7 +1046,7 @@ static cvb_status job_setup_p2p(Job *j) {
     if (mode && strcmp(mode, "nccl") == 0) return CVB_OK;  // keep NCCL in the step loop (comparison / fallback)
     if (c->nranks > MAX_RANKS) return CVB_OK;
     const int nplanes = g.count * g.nch;
-    const size_t pm_bytes = (size_t)nplanes * g.plane_elems * sizeof(double);
+    const size_t pm_bytes = ((size_t)nplanes * g.plane_elems + (size_t)TAIL_ROWS * g.pitch) * sizeof(double);
     for (int b = 0; b < 2; ++b)
         if (!j->d_pm[b]) {
             CU(c, cudaMalloc(&j->d_pm[b], pm_bytes));

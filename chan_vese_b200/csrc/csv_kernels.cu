@@ -15,6 +15,7 @@
 // ahead and L2 prefetch CSV_PF rows ahead.
 #include <string.h>
 
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "kernels.h"
 #include "math.cuh"
@@ -121,15 +122,6 @@ constexpr int RING_IMG = RING_U + 33 * 16;
 constexpr int RING_BYTES = RING_NS * RING_SLOT;
 static_assert(RING_IMG + 80 * MAX_CH <= RING_SLOT, "slot too small");
 static_assert(RING_NS - 1 <= TAIL_ROWS, "tail padding too small for the ring");
-
-__device__ __forceinline__ void cp_async16(unsigned int dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 template <int NCH, bool EDGE, bool LINEAR>
 __device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, double *__restrict__ uout,

@@ -12,6 +12,7 @@
 // a strip owns 60 columns, a 4-warp CTA 240.
 #include <string.h>
 
+#include "async_copy.cuh"
 #include "comm.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -205,6 +206,167 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
         IS = X;
         gC = gS;
     }
+}
+
+// ---- fast path with an asynchronous shared-memory row ring (fp64 input planes) ---------------------------
+// As csv_rows_ring: rows travel HBM -> shared memory with cp.async, ~8 rows ahead of their use, two rows per commit
+// group; the east / west neighbours of a row are read from the ring (6 of the 10 shuffles per row go away) and no
+// registers are held by loads in flight.  Ring row k holds image row ra-2+k in slot k % PM_RING_NS:
+//   [16 + 16*j, +16)  chunk j = 0..31: columns cs-2+2j, cs-1+2j (lane j's two columns)
+// Everything that is carried from row to row has period 2 or 3, and the loop is unrolled 6x: no register moves; with
+// PM_RING_NS = 12 the slot offsets are compile-time constants on top of a base that alternates between 0 and 6 slots.
+// The arithmetic is that of pm_rows_fast, operation for operation.
+constexpr int PM_RING_NS = 12;
+constexpr int PM_RING_SLOT = 16 + 32 * 16 + 16;
+constexpr int PM_RING_BYTES = PM_RING_NS * PM_RING_SLOT;
+static_assert(PM_RING_NS + 2 <= TAIL_ROWS + HALO, "tail padding too small for the PM ring");
+
+// LASTSEG: the segment ends at the image bottom (the only place where g = 1 must be forced inside the loop, :516).
+template <typename TOUT, bool EDGE, bool LASTSEG>
+__device__ __forceinline__ void pm_rows_ring(const double *__restrict__ in, TOUT *__restrict__ out, const Geom &G,
+                                             unsigned char *ring, int ra, int rb, int a, int lane, double inv_k2, double lq) {
+    const int w = G.w;
+    const bool colok = !EDGE || (a >= 0 && a < G.pitch);
+    const bool bc0 = EDGE && (a == 0 || a == w - 1), bc1 = EDGE && a + 1 == w - 1;  // border columns
+    const bool nofxw = EDGE && a == 0, nofx0 = EDGE && a == w - 1;
+    auto fixg = [&](double2 &g) {
+        if (EDGE) {
+            g.x = bc0 ? 1.0 : g.x;
+            g.y = bc1 ? 1.0 : g.y;
+        }
+    };
+    const size_t pitch = (size_t)G.pitch;
+    const double *pin = in + (size_t)(ra - 2 - G.row_lo + HALO) * pitch + a;  // row ra-2 = ring row 0
+    TOUT *po = out + (size_t)(ra - G.row_lo + HALO) * pitch + a;              // row ra
+    const int n = rb - ra;
+    const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring) + 16 + 16 * lane;
+    const unsigned char *my = ring + 16 + 16 * lane;  // + slot: own chunk; west neighbour at -8, east at +16
+
+    auto issue = [&](unsigned int slot_off) {  // the next ring row
+        if (colok) cp_async16(ring_s + slot_off, pin);
+        pin += pitch;
+    };
+    struct Row {
+        double2 X;
+        double Wn, E2;
+    };
+    auto fetch = [&](unsigned int slot_off) {
+        Row r;
+        r.X = *reinterpret_cast<const double2 *>(my + slot_off);
+        r.Wn = *reinterpret_cast<const double *>(my + slot_off - 8);
+        r.E2 = *reinterpret_cast<const double *>(my + slot_off + 16);
+        return r;
+    };
+    auto sobel_rows = [&](const Row &r, double2 &rd, double2 &rs) {  // separable Sobel, row pass
+        rd.x = r.X.y - r.Wn;
+        rs.x = fma(2.0, r.X.x, r.Wn) + r.X.y;
+        rd.y = r.E2 - r.X.x;
+        rs.y = fma(2.0, r.X.y, r.X.x) + r.E2;
+    };
+    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, gy * gy), inv_k2, 1.0)); };  // :518-521
+
+    // ring rows 0 .. NS-1, two per group
+#pragma unroll
+    for (int k = 0; k < PM_RING_NS; k += 2) {
+        issue(k * PM_RING_SLOT);
+        issue((k + 1) * PM_RING_SLOT);
+        cp_async_commit();
+    }
+    cp_async_wait<PM_RING_NS / 2 - 2>();  // ring rows 0..3 have landed
+    __syncwarp();
+    // prologue: rows ra-2 .. ra+1 give g(ra-1), g(ra) and the flux Fy(ra-1/2)
+    const Row Q0 = fetch(0), Q1 = fetch(PM_RING_SLOT), Q2 = fetch(2 * PM_RING_SLOT), Q3 = fetch(3 * PM_RING_SLOT);
+    double2 rd0, rs0, rd1, rs1, rd2, rs2, rd3, rs3;
+    sobel_rows(Q0, rd0, rs0);
+    sobel_rows(Q1, rd1, rs1);
+    sobel_rows(Q2, rd2, rs2);
+    sobel_rows(Q3, rd3, rs3);
+    double2 gP, gC;  // g(ra-1), g(ra)
+    gP.x = edge((rd0.x + 2.0 * rd1.x) + rd2.x, rs2.x - rs0.x);
+    gP.y = edge((rd0.y + 2.0 * rd1.y) + rd2.y, rs2.y - rs0.y);
+    gC.x = edge((rd1.x + 2.0 * rd2.x) + rd3.x, rs3.x - rs1.x);
+    gC.y = edge((rd1.y + 2.0 * rd2.y) + rd3.y, rs3.y - rs1.y);
+    if (ra == 0 || ra == G.h - 1) gC = make_double2(1.0, 1.0);  // g = 1 on the image border rows (:516)
+    fixg(gP);
+    fixg(gC);
+    double fy0 = (gP.x + gC.x) * (Q2.X.x - Q1.X.x), fy1 = (gP.y + gC.y) * (Q2.X.y - Q1.X.y);  // Fy(ra-1/2)
+    double2 IC = Q2.X, IS = Q3.X;                                              // rows i, i+1
+    double ICe = Q2.E2, ISe = Q3.E2;                                           // their east neighbours (column a+2)
+    double2 P = make_double2(fma(2.0, rd3.x, rd2.x), fma(2.0, rd3.y, rd2.y));  // rd(i) + 2 rd(i+1)
+    double2 rdB = rd3;                                                         // rd(i+1)
+    double2 rsA = rs2, rsB = rs3;                                              // rs(i), rs(i+1)
+    int r = 0;
+
+    // one output row i = ra + r: ring row r+4 (row i+2) arrives from slot s_x
+    auto row = [&](unsigned int s_x) {
+        const Row Q = fetch(s_x);
+        // g(i+1) from the Sobel sums of rows i, i+1, i+2 (:503-504, :513-522)
+        double2 rdC, rsC;
+        sobel_rows(Q, rdC, rsC);
+        double2 gS;
+        gS.x = edge(P.x + rdC.x, rsC.x - rsA.x);
+        gS.y = edge(P.y + rdC.y, rsC.y - rsA.y);
+        if (LASTSEG && ra + r + 1 == G.h - 1) gS = make_double2(1.0, 1.0);  // g = 1 on the last image row (:516)
+        fixg(gS);
+        // fluxes of row i and the update (:524-548); at the image top/bottom the halo rows hold copies of the border
+        // rows (clamped neighbours, :527-528), so the fluxes across the border are exactly zero
+        const double fs0 = (gC.x + gS.x) * (IS.x - IC.x), fs1 = (gC.y + gS.y) * (IS.y - IC.y);  // Fy(i+1/2)
+        const double ge = __shfl_down_sync(0xffffffffu, gC.x, 1);
+        double fx0 = (gC.x + gC.y) * (IC.y - IC.x);        // Fx(a+1/2)
+        double fx1 = (gC.y + ge) * (ICe - IC.y);           // Fx(a+3/2)
+        if (EDGE) {
+            fx0 = nofx0 ? 0.0 : fx0;
+            fx1 = bc1 ? 0.0 : fx1;
+        }
+        double fxw = __shfl_up_sync(0xffffffffu, fx1, 1);  // Fx(a-1/2)
+        if (EDGE) fxw = nofxw ? 0.0 : fxw;
+        const double o0 = fma((fs0 - fy0) + (fx0 - fxw), lq, IC.x);
+        const double o1 = fma((fs1 - fy1) + (fx1 - fx0), lq, IC.y);
+        if (EDGE) {
+            if (lane >= 1 && lane <= 30 && a < w) pm_store(po, o0, o1, a + 1 < w);
+        } else if (lane >= 1 && lane <= 30) {
+            pm_store(po, o0, o1, true);
+        }
+        po += pitch;
+        ++r;
+        // next row
+        fy0 = fs0;
+        fy1 = fs1;
+        P.x = fma(2.0, rdC.x, rdB.x);
+        P.y = fma(2.0, rdC.y, rdB.y);
+        rdB = rdC;
+        rsA = rsB;
+        rsB = rsC;
+        IC = IS;
+        ICe = ISe;
+        IS = Q.X;
+        ISe = Q.E2;
+        gC = gS;
+    };
+    // two rows: refill the two slots freed longest ago (ring rows r, r+1 -> r+NS, r+NS+1), wait for ring rows r+4, r+5
+    auto pair = [&](unsigned int s_w0, unsigned int s_x0, unsigned int s_x1) {
+        issue(s_w0);
+        issue(s_w0 + PM_RING_SLOT);
+        cp_async_commit();
+        cp_async_wait<PM_RING_NS / 2 - 2>();
+        __syncwarp();
+        row(s_x0);
+        row(s_x1);
+    };
+    constexpr unsigned int S = PM_RING_SLOT, H = 6 * PM_RING_SLOT;
+    unsigned int tog = 0;  // offset of the slot of ring row r: 0 or 6 slots
+#pragma unroll 1
+    while (r + 6 <= n) {
+        const unsigned int t2 = H - tog;
+        pair(tog, tog + 4 * S, tog + 5 * S);
+        pair(tog + 2 * S, t2, t2 + S);
+        pair(tog + 4 * S, t2 + 2 * S, t2 + 3 * S);
+        tog = t2;
+    }
+    cp_async_wait<0>();  // the rows of the tail (<= 5) have all been requested
+    __syncwarp();
+#pragma unroll 1
+    while (r < n) row((unsigned int)((r + 4) % PM_RING_NS) * S);
 }
 
 template <typename TIN, typename TOUT, bool STRICT>
@@ -403,7 +565,21 @@ __global__ void __launch_bounds__(CTA_THREADS, PM_MIN_CTAS) pm_step_kernel(const
     const double inv_k2 = A.inv_k2, lq = L * 0.25;
     // CTAs whose stencils stay inside the image take the fast path (all but the outermost ring)
     const bool interior = !STRICT && cb >= 1 && (cb + 1) * PM_CB + 2 <= w;  // image top/bottom included (replicated halo rows)
-    if (interior) {
+    constexpr bool RING = !STRICT && sizeof(TIN) == 8;  // fp64 input planes stream through the shared-memory ring
+    __shared__ __align__(16) unsigned char s_ring[RING ? PM_RING_BYTES : 16];
+    if (RING) {
+        const double *ind = reinterpret_cast<const double *>(in);
+        if (rb >= h - 1) {  // rows h-2 and h-1 need g(h-1) = 1
+            if (interior)
+                pm_rows_ring<TOUT, false, true>(ind, out, G, s_ring, ra, rb, a, lane, inv_k2, lq);
+            else
+                pm_rows_ring<TOUT, true, true>(ind, out, G, s_ring, ra, rb, a, lane, inv_k2, lq);
+        } else if (interior) {
+            pm_rows_ring<TOUT, false, false>(ind, out, G, s_ring, ra, rb, a, lane, inv_k2, lq);
+        } else {
+            pm_rows_ring<TOUT, true, false>(ind, out, G, s_ring, ra, rb, a, lane, inv_k2, lq);
+        }
+    } else if (interior) {
         pm_rows_fast<TIN, TOUT, false>(in, out, G, ra, rb, a, lane, inv_k2, lq);
     } else if (!STRICT) {
         pm_rows_fast<TIN, TOUT, true>(in, out, G, ra, rb, a, lane, inv_k2, lq);
@@ -427,6 +603,10 @@ static cudaError_t launch_pm_t(const PmArgs &A, bool strict, cudaStream_t s) {
         pm_step_kernel<TIN, TOUT, true><<<grid, CTA_THREADS, 0, s>>>(A);
     else {
         // programmatic dependent launch (see csv_kernels.cu): step n+1's CTAs become resident during the tail of step n
+        static cudaError_t carve = cudaFuncSetAttribute(pm_step_kernel<TIN, TOUT, false>,
+                                                        cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                        (int)cudaSharedmemCarveoutMaxShared);
+        if (carve != cudaSuccess) return carve;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(grid);
