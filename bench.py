@@ -160,6 +160,17 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.watchdog > 0:
+        # a rank that never comes back (a peer lost, a collective stuck) must not hold the box until the caller's own
+        # limit: report and leave -- os._exit tears the CUDA context down with the process
+        def give_up():
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world,
+                                  "error": "watchdog: no result after %d s" % args.watchdog}), flush=True)
+            os._exit(3)
+        wd = threading.Timer(args.watchdog, give_up)
+        wd.daemon = True
+        wd.start()
     h = w = args.size
     stream = torch.cuda.Stream()
     ctx = cv.Context(local, stream=stream.cuda_stream)
@@ -284,6 +295,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=1024, help="side of the CPU-baseline crop")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--tile-rows", type=int, default=0, help="rows per tile (0 = the library's automatic choice)")
+    ap.add_argument("--watchdog", type=int, default=420, help="give up after this many seconds (0 = never)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

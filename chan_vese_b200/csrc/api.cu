@@ -5,6 +5,7 @@
 #include <limits.h>
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -571,6 +572,20 @@ static cvb_status reduce_across_ranks(Job *j, const CsvArgs &A, int mode) {
     return CVB_OK;
 }
 
+// P2P row slabs: a device-side wait for a peer's flag gives up after SPIN_TIMEOUT_NS and marks the CommBox; report it
+// (the stream has been synchronised by the caller)
+static cvb_status check_peer_timeout(Job *j) {
+    cvb_context *c = j->ctx;
+    if (!j->p2p || !j->d_box) return CVB_OK;
+    unsigned int flag = 0;
+    CU(c, cudaMemcpy(&flag, reinterpret_cast<const char *>(j->d_box) + offsetof(CommBox, timed_out), sizeof flag,
+                     cudaMemcpyDeviceToHost));
+    if (flag)
+        return fail(c, CVB_ERR_COMM, "rank %d timed out waiting for a neighbouring rank's boundary rows / region sums",
+                    c->rank);
+    return CVB_OK;
+}
+
 static cvb_status job_upload_image(Job *j, const uint8_t *const *planes) {
     cvb_context *c = j->ctx;
     if (!planes) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes is NULL");
@@ -839,7 +854,7 @@ static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *st
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
     c->stats.pm_ms += ms;
-    return CVB_OK;
+    return check_peer_timeout(j);
 }
 
 // upload_image + perona_malik with the host-to-device copies hidden behind the diffusion of the planes that have
@@ -886,7 +901,7 @@ static cvb_status job_upload_image_smooth(Job *j, const uint8_t *const *planes, 
     CU(c, cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&pm_ms, c->ev[0], c->ev[1]);
     c->stats.pm_ms += pm_ms;  // includes the exposed part of the copies
-    return CVB_OK;
+    return check_peer_timeout(j);
 }
 static void job_release_pm(Job *j) {
     cudaFree(j->d_pm[0]);
@@ -987,7 +1002,7 @@ static cvb_status job_csv_run(Job *j, const cvb_csv_params *p, double tol, int m
         if (steps_done) steps_done[m] = j->h_state[m].steps_done;
         if (last_norm) last_norm[m] = j->h_state[m].norm;
     }
-    return CVB_OK;
+    return check_peer_timeout(j);
 }
 
 static cvb_status job_region_means(Job *j, double eps, double *c1, double *c2, int index) {

@@ -36,4 +36,28 @@ __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int *p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until the flag *p (written by a peer, only ever growing) reaches `need`.  Bounded: after SPIN_TIMEOUT_NS the
+// wait gives up, marks this rank's CommBox and returns false -- a lost peer becomes an error status on the host
+// (CVB_ERR_COMM) instead of a kernel that never ends.
+__device__ __forceinline__ bool spin_until(const unsigned int *p, unsigned int need, CommBox *box) {
+    if (ld_acquire_sys(p) >= need) return true;
+    if (ld_relaxed(&box->timed_out)) return false;
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 256; ++i)
+            if (ld_acquire_sys(p) >= need) return true;
+        if (global_ns() - t0 > SPIN_TIMEOUT_NS) {
+            *reinterpret_cast<volatile unsigned int *>(&box->timed_out) = 1u;
+            __threadfence();
+            return false;
+        }
+    }
+}
+
 }  // namespace cvb

@@ -76,7 +76,10 @@ struct CommBox {
     unsigned int pm_from_above;      // PM launches whose boundary rows the upper neighbour has pushed into my top halo
     unsigned int pm_from_below;
     unsigned int pm_ticket_up, pm_ticket_dn;  // boundary CTAs of the running PM launch that have finished
+    unsigned int timed_out;          // sticky: a wait for a peer's flag gave up after SPIN_TIMEOUT_NS (the host reports
+                                     // CVB_ERR_COMM instead of hanging; later waits return at once)
 };
+constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 struct CommView {
     int p2p;                         // 0: NCCL path (all-gather + send/recv issued by the host between launches)
     int nranks, rank;

@@ -508,7 +508,11 @@ __device__ __noinline__ void pm_push_boundary(const PmArgs &A, const TOUT *out, 
     __threadfence_system();
     __syncwarp();
     if (lane == 0) {
-        const unsigned int nb = (unsigned int)(G.ncb_pm * G.count * G.nch);  // boundary CTAs per side
+        // boundary CTAs per side: the first HALO rows lie in one segment (segments have >= 4 rows), the last HALO rows
+        // in two when the slab's last segment is a single row
+        const unsigned int nb = (unsigned int)(G.ncb_pm * G.count * G.nch);
+        const int last_rows = (G.row_hi - G.row_lo) - (G.pm_nseg - 1) * G.pm_seg_rows;
+        const unsigned int nb_dn = (G.pm_nseg > 1 && last_rows < HALO) ? 2u * nb : nb;
         if (top) {
             __threadfence();
             if (atomicAdd(&A.cv.box->pm_ticket_up, 1u) == nb - 1u) {
@@ -519,7 +523,7 @@ __device__ __noinline__ void pm_push_boundary(const PmArgs &A, const TOUT *out, 
         }
         if (bot) {
             __threadfence();
-            if (atomicAdd(&A.cv.box->pm_ticket_dn, 1u) == nb - 1u) {
+            if (atomicAdd(&A.cv.box->pm_ticket_dn, 1u) == nb_dn - 1u) {
                 A.cv.box->pm_ticket_dn = 0u;
                 __threadfence_system();
                 st_release_sys(&A.cv.peer_box[A.cv.rank + 1]->pm_from_above, A.cv.pm_seq);
@@ -529,13 +533,9 @@ __device__ __noinline__ void pm_push_boundary(const PmArgs &A, const TOUT *out, 
 }
 
 // One warp, between two PM launches of a P2P slab run: wait until both neighbours have pushed launch `need`.
-__global__ void pm_wait_kernel(const CommBox *box, unsigned int need, int has_up, int has_dn) {
-    if (threadIdx.x == 0 && has_up)
-        while (ld_acquire_sys(&box->pm_from_above) < need) {
-        }
-    if (threadIdx.x == 1 && has_dn)
-        while (ld_acquire_sys(&box->pm_from_below) < need) {
-        }
+__global__ void pm_wait_kernel(CommBox *box, unsigned int need, int has_up, int has_dn) {
+    if (threadIdx.x == 0 && has_up) spin_until(&box->pm_from_above, need, box);
+    if (threadIdx.x == 1 && has_dn) spin_until(&box->pm_from_below, need, box);
 }
 
 template <typename TIN, typename TOUT, bool STRICT>
@@ -629,7 +629,7 @@ cudaError_t launch_pm_step(const PmArgs &A, bool in_u8, bool out_u8, bool strict
     return launch_pm_t<double, double>(A, strict, s);
 }
 
-cudaError_t launch_pm_wait(const CommBox *box, unsigned int need, int has_up, int has_dn, cudaStream_t s) {
+cudaError_t launch_pm_wait(CommBox *box, unsigned int need, int has_up, int has_dn, cudaStream_t s) {
     pm_wait_kernel<<<1, 32, 0, s>>>(box, need, has_up, has_dn);
     return cudaGetLastError();
 }

@@ -79,9 +79,7 @@ __device__ __forceinline__ void csv_wait_fold(const CsvArgs &A) {
     const int lane = threadIdx.x & 31;
     const unsigned int prod = ld_relaxed(&b->produced);
     if (ld_relaxed(&b->finalized) == prod) return;  // nothing new (e.g. the image is frozen: launches were no-ops)
-    if (lane < A.cv.nranks)
-        while (ld_acquire_sys(&b->arrive[lane]) < prod) {
-        }
+    if (lane < A.cv.nranks) spin_until(&b->arrive[lane], prod, b);
     __syncwarp();
     __threadfence_system();
     csv_fold(A, 0, b->pending_mode, prod);
@@ -184,9 +182,7 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
     // ... and fold right here, in the tail of the same launch: this one warp waits until every rank has arrived (the
     // other SMs of this GPU are idle by now; the peers only need THEIR OWN launch to finish, so nobody waits in a
     // circle), then adds the group sums -- the same numbers in the same order on every rank.  No extra launch per step.
-    if (lane < A.cv.nranks)
-        while (ld_acquire_sys(&A.cv.box->arrive[lane]) < prod) {
-        }
+    if (lane < A.cv.nranks) spin_until(&A.cv.box->arrive[lane], prod, A.cv.box);
     __syncwarp();
     __threadfence_system();
     csv_fold(A, 0, final_mode, prod);
