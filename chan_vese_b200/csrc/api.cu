@@ -780,6 +780,10 @@ static cvb_status pm_run_planes(Job *j, int plane0, int np, double K, double L, 
     A.g.count = 1;  // the PM kernels only use count * nch = number of planes
     A.g.nch = np;
     A.cv = j->cv;
+    if (!j->p2p) {  // NCCL halo exchange between the launches: the launcher only needs to know that peers exist
+        A.cv.nranks = c->nranks;
+        A.cv.rank = c->rank;
+    }
     for (int b = 0; b < 2; ++b) {  // the kernels index the neighbours' buffers by plane - plane0, like their own
         if (A.cv.up_pm[b]) A.cv.up_pm[b] += (size_t)plane0 * (size_t)(A.cv.up_rows + 2 * HALO) * g.pitch;
         if (A.cv.dn_pm[b]) A.cv.dn_pm[b] += (size_t)plane0 * (size_t)(A.cv.dn_rows + 2 * HALO) * g.pitch;

@@ -327,14 +327,12 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     CsvState *st = A.state + img;
 #pragma unroll
     for (int q = 0; q < ATAN_TAB_N; q += 32) s_tab[q + lane] = make_double2(A.atan_tab[q + lane], atan_centre(q + lane));
-#ifndef CSV_NO_PDL
     if (MODE == MODE_STEP && !STRICT) {
         // launched with programmatic stream serialization: everything above is independent of the previous launch;
         // wait for it (c1/c2, stop flag, level set, halo rows), then let the next launch start filling freed slots
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;");
     }
-#endif
     const int2 ds = *reinterpret_cast<const int2 *>(&st->done);  // {done, steps_done}
     if (MODE == MODE_STEP && ds.x) return;  // frozen image: the launch is a no-op (src/main.cpp:1000)
     __syncwarp();
@@ -755,17 +753,18 @@ static cudaError_t launch_step_n(const CsvArgs &A, bool strict, int mode, cudaSt
         if (strict)
             csv_step_kernel<NCH, true, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
         else {
-#ifdef CSV_NO_PDL
-            csv_step_kernel<NCH, false, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
-#else
-            // Programmatic dependent launch: the CTAs of step n+1 may become resident while the tail of step n (last
-            // wave, group reductions, multi-GPU fold) is still running; they load the atan table and then block in
-            // griddepcontrol.wait until step n has completed and flushed.
             // 16 resident one-warp CTAs x (row ring + atan table) need ~210 KB of shared memory per SM
             static cudaError_t carve = cudaFuncSetAttribute(csv_step_kernel<NCH, false, MODE_STEP>,
                                                             cudaFuncAttributePreferredSharedMemoryCarveout,
                                                             (int)cudaSharedmemCarveoutMaxShared);
             if (carve != cudaSuccess) return carve;
+            if (!use_pdl(A.multi_rank != 0)) {
+                csv_step_kernel<NCH, false, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
+                return cudaGetLastError();
+            }
+            // Programmatic dependent launch: the CTAs of step n+1 may become resident while the tail of step n (last
+            // wave, group reductions) is still running; they load the atan table and then block in
+            // griddepcontrol.wait until step n has completed and flushed.
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
             cfg.gridDim = dim3(grid);
@@ -777,7 +776,6 @@ static cudaError_t launch_step_n(const CsvArgs &A, bool strict, int mode, cudaSt
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             return cudaLaunchKernelEx(&cfg, csv_step_kernel<NCH, false, MODE_STEP>, A);
-#endif
         }
     }
     return cudaGetLastError();

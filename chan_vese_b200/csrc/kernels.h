@@ -3,10 +3,22 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace cvb {
+
+// Programmatic dependent launch of the step kernels (the next step's CTAs become resident during the tail of the running
+// one).  On for single-GPU jobs (small-image step latency -15..25 %); OFF for multi-rank row slabs, whose step kernels
+// end in a wait for the peers: CVB_PDL=0/1 overrides either default.
+inline bool use_pdl(bool multi_rank) {
+    static const int env = [] {
+        const char *e = getenv("CVB_PDL");
+        return e ? (e[0] == '0' ? 0 : 1) : -1;
+    }();
+    return env >= 0 ? env == 1 : !multi_rank;
+}
 
 cudaError_t launch_csv_step(const CsvArgs &A, bool strict, cudaStream_t s);
 cudaError_t launch_csv_kappa(const CsvArgs &A, bool strict, cudaStream_t s);

@@ -607,6 +607,10 @@ static cudaError_t launch_pm_t(const PmArgs &A, bool strict, cudaStream_t s) {
                                                         cudaFuncAttributePreferredSharedMemoryCarveout,
                                                         (int)cudaSharedmemCarveoutMaxShared);
         if (carve != cudaSuccess) return carve;
+        if (!use_pdl(A.cv.nranks > 1)) {
+            pm_step_kernel<TIN, TOUT, false><<<grid, CTA_THREADS, 0, s>>>(A);
+            return cudaGetLastError();
+        }
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3(grid);
