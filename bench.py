@@ -224,7 +224,7 @@ def run_b200(args):
             fn()
         barrier()
         ctx.reset_stats()
-        sampler = ClockSampler(local) if sample_clocks else None
+        sampler = ClockSampler(local) if sample_clocks and rank == 0 else None  # one nvidia-smi poller per box
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
