@@ -295,7 +295,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=1024, help="side of the CPU-baseline crop")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--tile-rows", type=int, default=0, help="rows per tile (0 = the library's automatic choice)")
-    ap.add_argument("--watchdog", type=int, default=420, help="give up after this many seconds (0 = never)")
+    ap.add_argument("--watchdog", type=int, default=300, help="give up after this many seconds (0 = never)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

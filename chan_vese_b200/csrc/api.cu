@@ -780,7 +780,7 @@ static cvb_status pm_run_planes(Job *j, int plane0, int np, double K, double L, 
     A.g.count = 1;  // the PM kernels only use count * nch = number of planes
     A.g.nch = np;
     A.cv = j->cv;
-    if (!j->p2p) {  // NCCL halo exchange between the launches: the launcher only needs to know that peers exist
+    if (!j->p2p && j->slab) {  // NCCL halo exchange between the launches: the launcher only needs to know that peers exist
         A.cv.nranks = c->nranks;
         A.cv.rank = c->rank;
     }
