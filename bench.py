@@ -171,6 +171,11 @@ def run_b200(args):
         wd = threading.Timer(args.watchdog, give_up)
         wd.daemon = True
         wd.start()
+    def trace(msg):  # CVB_BENCH_TRACE=1: one stderr line per phase and rank (where does a multi-rank run stop?)
+        if os.environ.get("CVB_BENCH_TRACE"):
+            print("[rank %d %.1fs] %s" % (rank, time.time() - t_start, msg), file=sys.stderr, flush=True)
+
+    t_start = time.time()
     h = w = args.size
     stream = torch.cuda.Stream()
     ctx = cv.Context(local, stream=stream.cuda_stream)
@@ -195,8 +200,10 @@ def run_b200(args):
     mask_pin = torch.empty((rows, (w + 7) // 8), dtype=torch.uint8).pin_memory()
     mask_view = mask_pin.numpy()
     prm = cv.make_params()
+    trace("session created, slab rows [%d, %d), tile rows %d" % (lo, hi, tile_rows))
     sess.upload_image(views)
     sess.save_image()
+    trace("image uploaded")
 
     def step_resident():
         sess.restore_image()
@@ -220,8 +227,9 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, sample_clocks):
-        for _ in range(warmup):
+        for k in range(warmup):
             fn()
+            trace("%s: warm-up step %d done" % (fn.__name__, k))
         barrier()
         ctx.reset_stats()
         sampler = ClockSampler(local) if sample_clocks and rank == 0 else None  # one nvidia-smi poller per box
@@ -232,6 +240,7 @@ def run_b200(args):
         for _ in range(steps):
             n_pm, n_csv = fn()
         e1.record(stream)
+        trace("%s: %d timed steps enqueued and returned" % (fn.__name__, steps))
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
