@@ -578,8 +578,9 @@ static cvb_status check_peer_timeout(Job *j) {
     cvb_context *c = j->ctx;
     if (!j->p2p || !j->d_box) return CVB_OK;
     unsigned int flag = 0;
-    CU(c, cudaMemcpy(&flag, reinterpret_cast<const char *>(j->d_box) + offsetof(CommBox, timed_out), sizeof flag,
-                     cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpyAsync(&flag, reinterpret_cast<const char *>(j->d_box) + offsetof(CommBox, timed_out), sizeof flag,
+                          cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     if (flag)
         return fail(c, CVB_ERR_COMM, "rank %d timed out waiting for a neighbouring rank's boundary rows / region sums",
                     c->rank);
