@@ -872,7 +872,11 @@ static cvb_status job_upload_image_smooth(Job *j, const uint8_t *const *planes, 
     const int nplanes = g.count * g.nch;
     int nsteps = 0;
     TRY(pm_prepare(j, K, L, T, steps, &nsteps));
-    if ((j->slab && !j->p2p && j->ctx->nranks > 1) || nsteps == 0 || nplanes < 2) {  // nothing to overlap: the plain sequence
+    static const bool no_overlap = [] {  // CVB_OVERLAP_UPLOAD=0: the plain sequence (a switch for bisecting)
+        const char *e = getenv("CVB_OVERLAP_UPLOAD");
+        return e && e[0] == '0';
+    }();
+    if (no_overlap || (j->slab && !j->p2p && j->ctx->nranks > 1) || nsteps == 0 || nplanes < 2) {  // nothing to overlap
         TRY(job_upload_image(j, planes));
         return nsteps ? job_perona_malik(j, K, L, T, nullptr) : CVB_OK;
     }
