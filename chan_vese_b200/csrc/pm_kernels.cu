@@ -6,10 +6,12 @@
 // ~9 full-array passes).  The first step reads the uint8 image directly, the last one rounds to uint8
 // (saturate_cast, :551), so no separate conversion passes exist.
 //
-// Mapping: as in csv_kernels.cu a warp marches down a strip of 64 columns, two per lane.  Rows i-1..i+2
-// of I, three rows of the separable Sobel row sums and three rows of g live in registers; west/east
-// neighbours come from warp shuffles.  The stencil has radius 2, so lanes 0 and 31 are halo lanes:
-// a strip owns 60 columns, a 4-warp CTA 240.
+// Mapping: as in csv_kernels.cu a warp (= one CTA) marches down a strip of 64 columns, two per lane.  Rows i..i+2
+// of I, the separable Sobel row sums and two rows of g live in registers.  The stencil has radius 2, so lanes 0 and
+// 31 are halo lanes: a strip owns 60 columns.  fp64 planes stream through a cp.async shared-memory ring
+// (pm_rows_ring: east / west neighbours of I are read from the ring, g and the west flux come from the neighbouring
+// lanes by shuffle); the uint8-input first step and the strict path march rows through registers (pm_rows_fast,
+// pm_rows_generic).
 #include <string.h>
 
 #include "async_copy.cuh"
