@@ -227,10 +227,13 @@ extern "C" cvb_status cvb_levelset_circ(int h, int w, int cx, int cy, int radius
 // pick the one whose wave count wastes the least ("wave quantisation"; at 16384^2 on 8 GPUs 128-row segments give
 // 1.79 waves = 10 % idle, 79-row segments 2.91 waves = 3 %).  Small jobs keep >= 2 waves with at least 4 rows.
 static const int kSlots = 148 * 16;
-static int wave_aware_rows(int rows_per_rank, long long ctas_per_seg) {
+// min_tail > 0: lengths that leave a last segment of fewer than min_tail rows are not considered.
+static int wave_aware_rows(int rows_per_rank, long long ctas_per_seg, int min_tail = 0) {
     int best = 0;
     double best_eff = -1.0;
     for (int r = 192; r >= 48; --r) {
+        const int tail = rows_per_rank % r;
+        if (tail != 0 && tail < min_tail) continue;
         const long long ctas = (long long)ceil_div(rows_per_rank, r) * ctas_per_seg;
         const double waves = (double)ctas / kSlots;
         if (waves < 2.0) continue;
@@ -252,13 +255,19 @@ static int auto_seg_rows(int h, int w, int count, int nranks) {
         if ((long long)count * ceil_div(rows, s) * ncb >= 2LL * kSlots) return s;
     return 4;
 }
-static int auto_pm_seg_rows(int rows, int w, int planes) {
+// min_tail = HALO for the row slabs of a multi-rank run: the slab's last HALO rows should lie in ONE segment (they are
+// pushed to the neighbour by the CTAs of that segment; pm_push_boundary copes with a one-row last segment, but there is
+// no need to make one).  0 otherwise: whole images keep the plain choice.
+static int auto_pm_seg_rows(int rows, int w, int planes, int min_tail) {
     const int ncb = ceil_div(w, PM_CB);
-    const int r = wave_aware_rows(rows, (long long)planes * ncb);
+    auto tail_ok = [&](int s) { return rows % s == 0 || rows % s >= min_tail; };
+    const int r = wave_aware_rows(rows, (long long)planes * ncb, min_tail);
     if (r > 0) return r;
     const int cands[] = {32, 16, 8, 4};
     for (int s : cands)
-        if ((long long)planes * ceil_div(rows, s) * ncb >= 2LL * kSlots) return s;
+        if ((long long)planes * ceil_div(rows, s) * ncb >= 2LL * kSlots && tail_ok(s)) return s;
+    for (int s : {4, 5, 6, 7})
+        if (tail_ok(s)) return s;
     return 4;
 }
 extern "C" int cvb_auto_tile_rows(int h, int w, int count, int nranks) {
@@ -486,7 +495,7 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     g.ncb_csv = ceil_div(w, CSV_CB);
     g.ncb_pm = ceil_div(w, PM_CB);
     // PM has no reductions, so its segments need not follow the reduction groups: own wave-aware segment length
-    g.pm_seg_rows = auto_pm_seg_rows(row_hi - row_lo, w, count * n);
+    g.pm_seg_rows = auto_pm_seg_rows(row_hi - row_lo, w, count * n, (slab && c->nranks > 1) ? HALO : 0);
     g.pm_nseg = ceil_div(row_hi - row_lo, g.pm_seg_rows);
     g.plane_elems = (long long)g.rows_alloc * g.pitch;
     if ((long long)count * n * std::max(g.nseg, g.pm_nseg) * std::max(g.ncb_csv, g.ncb_pm) > 0x7fffffffLL)
