@@ -43,6 +43,7 @@ SIGNATURES = {
     "cvb_context_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "cvb_context_reset_stats": (C.c_int, [vp]),
     "cvb_context_synchronize": (C.c_int, [vp]),
+    "cvb_context_trim": (C.c_int, [vp]),
     "cvb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "cvb_host_free": (None, [vp]),
     "cvb_pm_num_steps": (C.c_int, [C.c_double, C.c_double]),
@@ -93,6 +94,7 @@ SIGNATURES = {
     "cvb_batch_download_image": (C.c_int, [vp, C.c_int, u8pp]),
     "cvb_batch_mask": (C.c_int, [vp, C.c_int, C.c_int, u8p]),
     "cvb_batch_mask_packed": (C.c_int, [vp, C.c_int, C.c_int, u8p]),
+    "cvb_batch_masks_packed": (C.c_int, [vp, C.c_int, u8p]),
     "cvb_batch_upload_images_smooth": (C.c_int, [vp, u8pp, C.c_double, C.c_double, C.c_double, intp]),
     "cvb_batch_save_images": (C.c_int, [vp]),
     "cvb_batch_restore_images": (C.c_int, [vp]),

@@ -84,6 +84,9 @@ struct cvb_context {
     // multi-GPU
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // the session behind the one-shot calls: kept between calls of the same shape, so that a caller looping over
+    // cvb_segment / cvb_csv_run / ... does not pay a cudaMalloc + cudaFree of every plane per call (cvb_context_trim frees it)
+    struct cvb_session *oneshot = nullptr;
 };
 
 struct Job {
@@ -98,8 +101,12 @@ struct Job {
     CsvState *d_state = nullptr;
     CsvState *h_state = nullptr;  // pinned, 2 * count
     double *d_partials = nullptr;
+    double *d_seg_sums = nullptr;          // one sum per row segment (reduce.cuh)
+    unsigned int *d_seg_ticket = nullptr;
+    int seg_level = 0;
     double *d_group = nullptr;
     signed char *d_sign = nullptr;  // checkerboard sign vectors
+    uint8_t *d_bits = nullptr;      // packed masks of a whole batch (cvb_batch_masks_packed), lazy
     int ngroups_local = 0;
     int group_lo = 0, group_hi = NGROUPS;  // groups owned by this rank
     bool slab = false;
@@ -245,14 +252,52 @@ static int wave_aware_rows(int rows_per_rank, long long ctas_per_seg, int min_ta
     }
     return best;
 }
-static int auto_seg_rows(int h, int w, int count, int nranks) {
+// Modelled efficiency of tile length r for an image cut into nranks row slabs (cvb_slab_partition): the rank with the
+// most segments sets the pace; waves / ceil(waves) x priming overhead.  0 when the slabs have fewer than two waves.
+// (most < ...: the model is about whole waves of equal CTAs; 1.5 waves is the least it is trusted with)
+static double slab_tile_eff(int h, int ncb, int r, int nranks) {
+    const int nseg = ceil_div(h, r);
+    int most = 0;
+    for (int k = 0; k < nranks; ++k) {
+        const int s0 = group_seg_begin(k * (NGROUPS / nranks), nseg), s1 = group_seg_begin((k + 1) * (NGROUPS / nranks), nseg);
+        most = std::max(most, s1 - s0);
+    }
+    const double waves = (double)most * ncb / kSlots;
+    if (waves < 1.5) return 0.0;
+    const double ideal = (double)h / nranks * ncb / kSlots;  // in rows per slot
+    return ideal / (ceil(waves) * (r + 3.5));
+}
+// Rows per tile of a single image.  The tiling fixes the order of the fused sums (reduce.cuh), so it must NOT depend on
+// the number of GPUs the image is spread over: a run on 1, 2, 4 or 8 GPUs then gives bit-identical results with the
+// automatic choice too.  The choice maximises the single-GPU efficiency plus the worst efficiency among the slab
+// decompositions (2, 4, 8 ranks) that are large enough to be worth running (>= 2 waves per rank).
+static int auto_seg_rows(int h, int w, int count, int /*nranks: deliberately unused*/) {
     const int ncb = ceil_div(w, CSV_CB);
-    const int rows = ceil_div(h, nranks < 1 ? 1 : nranks);
-    const int r = wave_aware_rows(rows, (long long)count * ncb);
+    if (count == 1) {
+        int best = 0;
+        double best_score = 0.0;
+        for (int r = 192; r >= 24; --r) {
+            const double e1 = slab_tile_eff(h, ncb, r, 1);
+            if (e1 <= 0.0) continue;
+            double worst = e1;
+            for (int n : {2, 4, 8}) {
+                if ((double)h / n * ncb / 48.0 < 2.0 * kSlots) continue;  // not worth a slab run at any tile length
+                const double e = slab_tile_eff(h, ncb, r, n);
+                worst = std::min(worst, e);
+            }
+            const double score = e1 + worst;
+            if (score > best_score + 1e-9) {
+                best_score = score;
+                best = r;
+            }
+        }
+        if (best > 0) return best;
+    }
+    const int r = wave_aware_rows(h, (long long)count * ncb);
     if (r > 0) return r;
     const int cands[] = {32, 16, 8, 4};
     for (int s : cands)
-        if ((long long)count * ceil_div(rows, s) * ncb >= 2LL * kSlots) return s;
+        if ((long long)count * ceil_div(h, s) * ncb >= 2LL * kSlots) return s;
     return 4;
 }
 // min_tail = HALO for the row slabs of a multi-rank run: the slab's last HALO rows should lie in ONE segment (they are
@@ -324,9 +369,17 @@ extern "C" cvb_status cvb_context_create(int device, void *stream, cvb_context *
     *out = c;
     return CVB_OK;
 }
+extern "C" void cvb_session_destroy(cvb_session *s);
+extern "C" cvb_status cvb_context_trim(cvb_context *c) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    cvb_session_destroy(c->oneshot);
+    c->oneshot = nullptr;
+    return CVB_OK;
+}
 extern "C" void cvb_context_destroy(cvb_context *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    cvb_context_trim(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_atan_tab);
     for (auto &e : c->ev)
@@ -338,6 +391,7 @@ extern "C" void cvb_context_destroy(cvb_context *c) {
     delete c;
 }
 extern "C" const char *cvb_last_error(const cvb_context *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+extern "C" cvb_status cvb_context_trim(cvb_context *c);
 extern "C" cvb_status cvb_context_set_math_mode(cvb_context *c, cvb_math_mode m) {
     if (!c || (m != CVB_MATH_FAST && m != CVB_MATH_STRICT)) return CVB_ERR_INVALID_ARGUMENT;
     c->math = m;
@@ -345,6 +399,7 @@ extern "C" cvb_status cvb_context_set_math_mode(cvb_context *c, cvb_math_mode m)
 }
 extern "C" cvb_status cvb_context_set_tile_rows(cvb_context *c, int rows) {
     if (!c || rows < 0 || rows > 4096) return CVB_ERR_INVALID_ARGUMENT;
+    if (rows != c->tile_rows && c->oneshot) cvb_context_trim(c);  // the cached one-shot session was tiled differently
     c->tile_rows = rows;
     return CVB_OK;
 }
@@ -448,8 +503,11 @@ static void job_free(Job *j) {
     cudaFree(j->d_aux);
     cudaFree(j->d_state);
     cudaFree(j->d_partials);
+    cudaFree(j->d_seg_sums);
+    cudaFree(j->d_seg_ticket);
     cudaFree(j->d_group);
     cudaFree(j->d_sign);
+    cudaFree(j->d_bits);
     if (!j->ipc_opened.empty()) {
         for (void *p : j->ipc_opened) cudaIpcCloseMemHandle(p);
         j->ipc_opened.clear();
@@ -527,6 +585,14 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     const size_t npart = (size_t)count * g.nseg * g.ncb_csv * WARPS_PER_CTA * NACC;
     CU(c, cudaMalloc(&j->d_partials, npart * sizeof(double)));
     CU(c, cudaMalloc(&j->d_group, 2 * (size_t)NGROUPS * count * NACC * sizeof(double)));
+    const size_t nsegs = (size_t)count * g.nseg;
+    CU(c, cudaMalloc(&j->d_seg_sums, nsegs * NACC * sizeof(double)));
+    CU(c, cudaMalloc(&j->d_seg_ticket, nsegs * sizeof(unsigned int)));
+    CU(c, cudaMemsetAsync(j->d_seg_sums, 0, nsegs * NACC * sizeof(double), c->stream));
+    CU(c, cudaMemsetAsync(j->d_seg_ticket, 0, nsegs * sizeof(unsigned int), c->stream));
+    // a reduction group of more than 128 partial vectors is summed per segment first; keyed to the GLOBAL geometry, so
+    // every slab of an image takes the same decision
+    j->seg_level = ((long long)ceil_div(g.nseg_global, NGROUPS) * g.ncb_csv > 128) ? 1 : 0;
     CU(c, cudaMallocHost(&j->h_state, 2 * (size_t)count * sizeof(CsvState)));
     CU(c, cudaMemsetAsync(j->d_img, 0, (size_t)count * n * pe + tail, c->stream));
     CU(c, cudaMemsetAsync(j->d_u[0], 0, ((size_t)count * pe + tail) * esz(j), c->stream));
@@ -545,6 +611,9 @@ static void fill_args(const Job *j, const cvb_csv_params *p, double tol, CsvArgs
     A.state = j->d_state;
     A.partials = j->d_partials;
     A.group_sums = j->d_group;
+    A.seg_sums = j->d_seg_sums;
+    A.seg_ticket = j->d_seg_ticket;
+    A.seg_level = j->seg_level;
     A.kappa_out = j->d_aux;
     A.atan_tab = j->ctx->d_atan_tab;
     A.eps = 1.0;
@@ -747,6 +816,25 @@ static cvb_status job_mask_packed(Job *j, int index, int invert, uint8_t *bits) 
     return CVB_OK;
 }
 
+// the packed masks of every image of the job with one launch and one device-to-host copy
+static cvb_status job_masks_packed_all(Job *j, int invert, uint8_t *bits) {
+    cvb_context *c = j->ctx;
+    if (!bits) return fail(c, CVB_ERR_INVALID_ARGUMENT, "bits is NULL");
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    if (g.count > 65535) return fail(c, CVB_ERR_INVALID_ARGUMENT, "masks_packed: more than 65535 images");
+    const int rows = g.row_hi - g.row_lo, wb = (g.w + 7) / 8;
+    const size_t bytes = (size_t)g.count * rows * wb;
+    if (!j->d_bits) CU(c, cudaMalloc(&j->d_bits, bytes));
+    CU(c, launch_mask_packed_batch(j->d_u[0], j->d_u[1], j->d_state, is_f32(j) ? 1 : 0, j->d_bits, g.count, rows, g.w, g.pitch,
+                                   (size_t)g.plane_elems * esz(j), invert, c->stream));
+    c->stats.kernel_launches += 1;
+    CU(c, cudaMemcpyAsync(bits, j->d_bits, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += bytes;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
+}
+
 static cvb_status job_init_checkerboard(Job *j) {
     cvb_context *c = j->ctx;
     CU(c, cudaSetDevice(c->device));
@@ -927,10 +1015,17 @@ static cvb_status job_upload_image_smooth(Job *j, const uint8_t *const *planes, 
     c->stats.pm_ms += pm_ms;  // includes the exposed part of the copies
     return check_peer_timeout(j);
 }
-static void job_release_pm(Job *j) {
+// A P2P slab session has exported its PM state buffers over CUDA IPC and the neighbours push boundary rows into them:
+// they live as long as the session (release is refused; freeing them would leave the peers with stale mappings).
+static cvb_status job_release_pm(Job *j) {
+    if (j->p2p)
+        return fail(j->ctx, CVB_ERR_STATE, "release_scratch: the Perona-Malik planes of a multi-GPU slab session are mapped by "
+                                           "the neighbouring ranks and stay allocated until the session is destroyed");
+    cudaStreamSynchronize(j->ctx->stream);
     cudaFree(j->d_pm[0]);
     cudaFree(j->d_pm[1]);
     j->d_pm[0] = j->d_pm[1] = nullptr;
+    return CVB_OK;
 }
 
 static cvb_status check_params(cvb_context *c, const cvb_csv_params *p) {
@@ -1243,10 +1338,7 @@ extern "C" cvb_status cvb_session_upload_image_smooth(cvb_session *s, const uint
 extern "C" cvb_status cvb_session_save_image(cvb_session *s) { return s ? job_save_image(s) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_session_restore_image(cvb_session *s) { return s ? job_restore_image(s) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_session_release_scratch(cvb_session *s) {
-    if (!s) return CVB_ERR_INVALID_ARGUMENT;
-    cudaStreamSynchronize(s->ctx->stream);
-    job_release_pm(s);
-    return CVB_OK;
+    return s ? job_release_pm(s) : CVB_ERR_INVALID_ARGUMENT;
 }
 
 // ---- batches ---------------------------------------------------------------------------------------------------
@@ -1298,6 +1390,9 @@ extern "C" cvb_status cvb_batch_mask(cvb_batch *b, int index, int invert, uint8_
 extern "C" cvb_status cvb_batch_mask_packed(cvb_batch *b, int index, int invert, uint8_t *bits) {
     return b ? job_mask_packed(b, index, invert, bits) : CVB_ERR_INVALID_ARGUMENT;
 }
+extern "C" cvb_status cvb_batch_masks_packed(cvb_batch *b, int invert, uint8_t *bits) {
+    return b ? job_masks_packed_all(b, invert, bits) : CVB_ERR_INVALID_ARGUMENT;
+}
 extern "C" cvb_status cvb_batch_upload_images_smooth(cvb_batch *b, const uint8_t *const *planes, double K, double L, double T,
                                                      int *steps) {
     return b ? job_upload_image_smooth(b, planes, K, L, T, steps) : CVB_ERR_INVALID_ARGUMENT;
@@ -1305,39 +1400,60 @@ extern "C" cvb_status cvb_batch_upload_images_smooth(cvb_batch *b, const uint8_t
 extern "C" cvb_status cvb_batch_save_images(cvb_batch *b) { return b ? job_save_image(b) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_batch_restore_images(cvb_batch *b) { return b ? job_restore_image(b) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_batch_release_scratch(cvb_batch *b) {
-    if (!b) return CVB_ERR_INVALID_ARGUMENT;
-    cudaStreamSynchronize(b->ctx->stream);
-    job_release_pm(b);
-    return CVB_OK;
+    return b ? job_release_pm(b) : CVB_ERR_INVALID_ARGUMENT;
 }
 
 // ---- one-shot calls on host buffers (the drop-in seams) ------------------------------------------------------
-struct SessionGuard {
+// The one-shot calls run on a whole-image fp64 session owned by the context and reused while the shape stays the same.
+static cvb_status oneshot_session(cvb_context *c, int n, int h, int w, cvb_session **out) {
+    cvb_session *s = c->oneshot;
+    if (s && (s->g.nch != n || s->g.h != h || s->g.w != w)) {
+        cvb_session_destroy(s);
+        s = c->oneshot = nullptr;
+    }
+    if (!s) {
+        TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &s));
+        c->oneshot = s;
+    }
+    *out = s;
+    return CVB_OK;
+}
+struct SessionGuard {  // the name is historic: the session is cached, a failed call drops it (its state is unknown)
+    cvb_context *c = nullptr;
     cvb_session *s = nullptr;
-    ~SessionGuard() { cvb_session_destroy(s); }
+    bool ok = false;
+    ~SessionGuard() {
+        if (!ok && c && c->oneshot) cvb_context_trim(c);
+    }
 };
+#define ONESHOT(g, c, n, h, w)  \
+    SessionGuard g;             \
+    g.c = c;                    \
+    TRY(oneshot_session(c, n, h, w, &g.s))
 
 extern "C" cvb_status cvb_perona_malik(cvb_context *c, const uint8_t *const *planes_in, int n, int h, int w, double K,
                                        double L, double T, uint8_t *const *planes_out, int *steps) {
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
     if (!planes_in || !planes_out) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes is NULL");
-    SessionGuard g;
-    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    ONESHOT(g, c, n, h, w);
     TRY(cvb_session_upload_image(g.s, planes_in));
     TRY(cvb_session_perona_malik(g.s, K, L, T, steps));
-    return cvb_session_download_image(g.s, planes_out);
+    TRY(cvb_session_download_image(g.s, planes_out));
+    g.ok = true;
+    return CVB_OK;
 }
 
 extern "C" cvb_status cvb_csv_run(cvb_context *c, const uint8_t *const *planes, int n, int h, int w, double *u_inout,
                                   const cvb_csv_params *params, double tol, int max_steps, int *steps_done,
                                   double *last_norm, cvb_frame_fn frame, void *user) {
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
-    SessionGuard g;
-    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    ONESHOT(g, c, n, h, w);
     TRY(cvb_session_upload_image(g.s, planes));
     TRY(cvb_session_upload_levelset(g.s, u_inout));
     TRY(cvb_session_csv_run(g.s, params, tol, max_steps, steps_done, last_norm, frame, user));
-    return cvb_session_download_levelset(g.s, u_inout);
+    TRY(cvb_session_download_levelset(g.s, u_inout));
+    g.ok = true;
+    return CVB_OK;
 }
 
 extern "C" cvb_status cvb_segment(cvb_context *c, const uint8_t *const *planes, int n, int h, int w, double *u_inout,
@@ -1345,8 +1461,7 @@ extern "C" cvb_status cvb_segment(cvb_context *c, const uint8_t *const *planes, 
                                   const cvb_csv_params *params, double tol, int max_steps, int *steps_done,
                                   double *last_norm, int invert, uint8_t *mask_out) {
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
-    SessionGuard g;
-    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    ONESHOT(g, c, n, h, w);
     TRY(cvb_session_upload_image(g.s, planes));
     TRY(cvb_session_upload_levelset(g.s, u_inout));
     if (smooth) {
@@ -1356,27 +1471,28 @@ extern "C" cvb_status cvb_segment(cvb_context *c, const uint8_t *const *planes, 
     TRY(cvb_session_csv_run(g.s, params, tol, max_steps, steps_done, last_norm, nullptr, nullptr));
     TRY(cvb_session_download_levelset(g.s, u_inout));
     if (mask_out) TRY(cvb_session_mask(g.s, invert, mask_out));
+    g.ok = true;
     return CVB_OK;
 }
 
 extern "C" cvb_status cvb_region_means(cvb_context *c, const uint8_t *const *planes, int n, int h, int w, const double *u,
                                        double eps, double *c1, double *c2) {
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
-    SessionGuard g;
-    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    ONESHOT(g, c, n, h, w);
     TRY(cvb_session_upload_image(g.s, planes));
     TRY(cvb_session_upload_levelset(g.s, u));
-    return cvb_session_region_means(g.s, eps, c1, c2);
+    TRY(cvb_session_region_means(g.s, eps, c1, c2));
+    g.ok = true;
+    return CVB_OK;
 }
 
 extern "C" cvb_status cvb_curvature(cvb_context *c, const double *u, int h, int w, double *kappa) {
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
     if (!u || !kappa) return fail(c, CVB_ERR_INVALID_ARGUMENT, "u / kappa is NULL");
-    SessionGuard g;
-    TRY(cvb_session_create(c, 1, h, w, CVB_PRECISION_F64, &g.s));
+    ONESHOT(g, c, 1, h, w);
     Job *j = g.s;
     TRY(cvb_session_upload_levelset(g.s, u));
-    CU(c, cudaMalloc(&j->d_aux, (size_t)j->g.plane_elems * sizeof(double)));
+    if (!j->d_aux) CU(c, cudaMalloc(&j->d_aux, (size_t)j->g.plane_elems * sizeof(double)));
     CsvArgs A;
     fill_args(j, nullptr, 0.0, A);
     CU(c, launch_csv_kappa(A, c->math == CVB_MATH_STRICT, c->stream));
@@ -1385,6 +1501,7 @@ extern "C" cvb_status cvb_curvature(cvb_context *c, const double *u, int h, int 
                             w * sizeof(double), h, cudaMemcpyDeviceToHost, c->stream));
     c->stats.d2h_bytes += (uint64_t)h * w * sizeof(double);
     CU(c, cudaStreamSynchronize(c->stream));
+    g.ok = true;
     return CVB_OK;
 }
 
@@ -1411,8 +1528,7 @@ extern "C" cvb_status cvb_stop_condition(cvb_context *c, const uint8_t *const *p
                                          double *stop) {
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
     if (!stop) return fail(c, CVB_ERR_INVALID_ARGUMENT, "stop is NULL");
-    SessionGuard g;
-    TRY(cvb_session_create(c, n, h, w, CVB_PRECISION_F64, &g.s));
+    ONESHOT(g, c, n, h, w);
     TRY(cvb_session_upload_image(g.s, planes));
     Job *j = g.s;
     cvb_csv_params p{};
@@ -1422,13 +1538,15 @@ extern "C" cvb_status cvb_stop_condition(cvb_context *c, const uint8_t *const *p
     TRY(job_csv_init(j, A, 1));
     TRY(job_fetch_state(j));
     *stop = j->h_state[0].stop;
+    g.ok = true;
     return CVB_OK;
 }
 
 extern "C" cvb_status cvb_mask(cvb_context *c, const double *u, int h, int w, int invert, uint8_t *mask) {
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
-    SessionGuard g;
-    TRY(cvb_session_create(c, 1, h, w, CVB_PRECISION_F64, &g.s));
+    ONESHOT(g, c, 1, h, w);
     TRY(cvb_session_upload_levelset(g.s, u));
-    return cvb_session_mask(g.s, invert, mask);
+    TRY(cvb_session_mask(g.s, invert, mask));
+    g.ok = true;
+    return CVB_OK;
 }

@@ -5,9 +5,12 @@
 //   rows_alloc x pitch elements, rows_alloc = (row_hi - row_lo) + 2*HALO, local row 0 = global row
 //   row_lo - HALO.  pitch is a multiple of 16 elements, so a thread's two adjacent columns form one
 //   aligned 16-byte (fp64) access and every row starts on a 128-byte line.  Halo rows hold the
-//   neighbouring slab's rows (multi-GPU) and are unused at the global image border, where indices
-//   are clamped (BORDER_REPLICATE / clamped neighbours of the reference, src/main.cpp:351-354,
-//   527-530).  Planes of one kind are contiguous: plane (image m, channel k) = base + (m*nch+k)*plane_elems.
+//   neighbouring slab's rows (multi-GPU).  INVARIANT at the global image border: the halo rows above
+//   row 0 and below row h-1 hold COPIES of the border row (BORDER_REPLICATE / clamped neighbours of
+//   the reference, src/main.cpp:351-354, 527-530) -- the production row rings read them instead of
+//   clamping indices.  Every path that writes a plane keeps it: the step kernels (replicate_border_rows,
+//   pm_replicate_border) and the upload / initialiser / restore paths (launch_replicate_halo).
+//   Planes of one kind are contiguous: plane (image m, channel k) = base + (m*nch+k)*plane_elems.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -97,6 +100,8 @@ struct CsvArgs {
     const uint8_t *img;     // count * nch planes
     CsvState *state;        // count
     double *partials;       // [count][nseg][ncb][NACC]
+    double *seg_sums;       // [count][nseg][NACC]: one sum per row segment (reduce.cuh, seg_level)
+    unsigned int *seg_ticket;  // [count][nseg]: CTAs of a segment that have delivered their partial vector
     double *group_sums;     // [2][NGROUPS][count][NACC] (second copy: P2P double buffering)
     double *kappa_out;      // MODE_KAPPA only
     const double *atan_tab; // ATAN_NQ entries, see math.cuh
@@ -107,6 +112,7 @@ struct CsvArgs {
     int multi_rank;         // 1: stop after the group sums; csv_finalize runs after the all-gather
     int par;                // parity of the step counter of every image that is still running (known to the host, so
                             // the first row loads need not wait for the state load); frozen images exit anyway
+    int seg_level;          // 1: partial vectors are summed per segment first (jobs with many vectors per group)
     int ngroups_local;      // non-empty groups owned by this rank
     int group_lo, group_hi; // groups owned by this rank
     Geom g;

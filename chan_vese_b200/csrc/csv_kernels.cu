@@ -225,8 +225,15 @@ __device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, do
         double I0[NCH], I1[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
+#ifdef CSV_I256
+            // 256 + I, exact, built in the integer pipe (the byte goes to mantissa bits 44..51 of 2^8): no FP64
+            // conversion; the coefficients and the sums below are written for I' = I + 256 (StepCoef, end of the loop)
+            I0[c] = __hiloint2double(0x40700000 | ((Ib[c] & 0xffu) << 12), 0);
+            I1[c] = __hiloint2double(0x40700000 | ((Ib[c] << 4) & 0xff000u), 0);
+#else
             I0[c] = u8_to_double(Ib[c] & 0xffu);
             I1[c] = u8_to_double(Ib[c] >> 8);
+#endif
         }
         double t0 = K.q0, t1 = K.q0;
 #pragma unroll
@@ -308,7 +315,11 @@ __device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, do
         acc[ACC_A] = accA;
         acc[ACC_SQ] = accS;
 #pragma unroll
+#ifdef CSV_I256
+        for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = fma(-256.0, accA, accI[c]);  // sum (I+256) a - 256 sum a
+#else
         for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = accI[c];
+#endif
     }
 }
 
@@ -393,6 +404,17 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
 #endif
     const double q0 = K.q0, alphap = K.alphap, eps2 = K.eps2;
     const double *cA = K.cA, *cB = K.cB;
+#ifdef CSV_I256
+    // the ring paths evaluate the data term in I' = I + 256:  A I^2 + B I + q0 = A I'^2 + (B - 512 A) I' + (q0 + 65536 A - 256 B)
+    StepCoef<NCH> K2 = K;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        K2.cB[k] = fma(-512.0, K.cA[k], K.cB[k]);
+        K2.q0 += fma(65536.0, K.cA[k], -256.0 * K.cB[k]);
+    }
+#else
+    const StepCoef<NCH> &K2 = K;
+#endif
 
     double acc[NACC];
 #pragma unroll
@@ -404,14 +426,14 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     const bool edge_fast = !STRICT && MODE == MODE_STEP && !interior && cs < w;
     if (interior) {
         if (K.linear)
-            csv_rows_ring<NCH, false, true>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
+            csv_rows_ring<NCH, false, true>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc);
         else
-            csv_rows_ring<NCH, false, false>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
+            csv_rows_ring<NCH, false, false>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc);
     } else if (edge_fast) {
         if (K.linear)
-            csv_rows_ring<NCH, true, true>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
+            csv_rows_ring<NCH, true, true>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc);
         else
-            csv_rows_ring<NCH, true, false>(uin, uout, im, G, K, s_tab, s_ring, ra, rb, cs, lane, acc);
+            csv_rows_ring<NCH, true, false>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc);
     } else if (cs < w) {
         const int nk = rb - ra + 3;  // streamed rows ra-2 .. rb
         double2 pq[CSV_D];
@@ -677,41 +699,70 @@ __global__ void delta_map_kernel(double *data, size_t n, double eps) {
 // separate()'s mask: float32(u) > 0, optionally inverted (src/main.cpp:395-400).  Pitched in, pitched out.
 __global__ void mask_kernel(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= w || i >= rows) return;
-    const size_t q = (size_t)i * pitch + j;
-    const uint8_t m = (__double2float_rn(u[q]) > 0.0f) ? 1 : 0;
-    mask[q] = invert ? (uint8_t)(1 - m) : m;
+    if (j >= w) return;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y) {  // gridDim.y is capped at 65535: taller planes loop
+        const size_t q = (size_t)i * pitch + j;
+        const uint8_t m = (__double2float_rn(u[q]) > 0.0f) ? 1 : 0;
+        mask[q] = invert ? (uint8_t)(1 - m) : m;
+    }
 }
 
 // the same mask, 8 pixels per byte (MSB first), rows padded to whole bytes; u is fp64 or fp32
 __global__ void mask_packed_kernel(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert) {
     const int jb = blockIdx.x * blockDim.x + threadIdx.x;  // byte within the row
-    const int i = blockIdx.y;
     const int wb = (w + 7) / 8;
-    if (jb >= wb || i >= rows) return;
-    unsigned int b = 0;
-    for (int k = 0; k < 8; ++k) {
-        const int j = jb * 8 + k;
-        unsigned int m = 0;
-        if (j < w) {
-            const float v = f32 ? reinterpret_cast<const float *>(u)[(size_t)i * pitch + j]
-                                : __double2float_rn(reinterpret_cast<const double *>(u)[(size_t)i * pitch + j]);
-            m = (v > 0.0f) ? 1u : 0u;
-            if (invert) m ^= 1u;
+    if (jb >= wb) return;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y) {
+        unsigned int b = 0;
+        for (int k = 0; k < 8; ++k) {
+            const int j = jb * 8 + k;
+            unsigned int m = 0;
+            if (j < w) {
+                const float v = f32 ? reinterpret_cast<const float *>(u)[(size_t)i * pitch + j]
+                                    : __double2float_rn(reinterpret_cast<const double *>(u)[(size_t)i * pitch + j]);
+                m = (v > 0.0f) ? 1u : 0u;
+                if (invert) m ^= 1u;
+            }
+            b |= m << (7 - k);
         }
-        b |= m << (7 - k);
+        bits[(size_t)i * wb + jb] = (uint8_t)b;
     }
-    bits[(size_t)i * wb + jb] = (uint8_t)b;
+}
+
+// every image of a batch at once: image m's current level set is in buffer (steps_done & 1) of its own state
+__global__ void mask_packed_batch_kernel(const char *u0, const char *u1, const CsvState *state, int f32, uint8_t *bits, int rows,
+                                         int w, int pitch, size_t plane_bytes, int invert) {
+    const int jb = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wb = (w + 7) / 8;
+    if (jb >= wb) return;
+    const int img = blockIdx.z;
+    const size_t esz = f32 ? 4 : 8;
+    const char *u = ((state[img].steps_done & 1) ? u1 : u0) + (size_t)img * plane_bytes + (size_t)HALO * pitch * esz;
+    uint8_t *out = bits + (size_t)img * rows * wb;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y) {
+        unsigned int b = 0;
+        for (int k = 0; k < 8; ++k) {
+            const int j = jb * 8 + k;
+            unsigned int m = 0;
+            if (j < w) {
+                const float v = f32 ? reinterpret_cast<const float *>(u)[(size_t)i * pitch + j]
+                                    : __double2float_rn(reinterpret_cast<const double *>(u)[(size_t)i * pitch + j]);
+                m = (v > 0.0f) ? 1u : 0u;
+                if (invert) m ^= 1u;
+            }
+            b |= m << (7 - k);
+        }
+        out[(size_t)i * wb + jb] = (uint8_t)b;
+    }
 }
 
 // u0(i,j) = si[i] * sj[j] with host-computed sign vectors (bit parity with glibc sin)
 __global__ void checkerboard_kernel(double *u, const signed char *si, const signed char *sj, int row_lo, int rows,
                                     int w, int pitch) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= w || i >= rows) return;
-    u[(size_t)(i + HALO) * pitch + j] = (double)((int)si[row_lo + i] * (int)sj[j]);
+    if (j >= w) return;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y)
+        u[(size_t)(i + HALO) * pitch + j] = (double)((int)si[row_lo + i] * (int)sj[j]);
 }
 
 // Fill the border halo rows of freshly written planes (upload, initialisers): rows -2,-1 := row 0 when the job owns
@@ -754,9 +805,7 @@ static cudaError_t launch_step_n(const CsvArgs &A, bool strict, int mode, cudaSt
             csv_step_kernel<NCH, true, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
         else {
             // 16 resident one-warp CTAs x (row ring + atan table) need ~210 KB of shared memory per SM
-            static cudaError_t carve = cudaFuncSetAttribute(csv_step_kernel<NCH, false, MODE_STEP>,
-                                                            cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                            (int)cudaSharedmemCarveoutMaxShared);
+            const cudaError_t carve = prefer_max_shared(csv_step_kernel<NCH, false, MODE_STEP>);
             if (carve != cudaSuccess) return carve;
             if (!use_pdl(A.multi_rank != 0)) {
                 csv_step_kernel<NCH, false, MODE_STEP><<<grid, CTA_THREADS, 0, s>>>(A);
@@ -807,18 +856,25 @@ cudaError_t launch_delta_map(double *data, size_t n, double eps, cudaStream_t s)
     return cudaGetLastError();
 }
 cudaError_t launch_mask(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s) {
-    dim3 grid((w + 255) / 256, rows);
+    dim3 grid((w + 255) / 256, std::min(rows, 65535));
     mask_kernel<<<grid, 256, 0, s>>>(u, mask, rows, w, pitch, invert);
     return cudaGetLastError();
 }
 cudaError_t launch_mask_packed(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, cudaStream_t s) {
-    dim3 grid(((w + 7) / 8 + 127) / 128, rows);
+    dim3 grid(((w + 7) / 8 + 127) / 128, std::min(rows, 65535));
     mask_packed_kernel<<<grid, 128, 0, s>>>(u, f32, bits, rows, w, pitch, invert);
+    return cudaGetLastError();
+}
+cudaError_t launch_mask_packed_batch(const void *u0, const void *u1, const CsvState *state, int f32, uint8_t *bits, int count,
+                                     int rows, int w, int pitch, size_t plane_bytes, int invert, cudaStream_t s) {
+    dim3 grid(((w + 7) / 8 + 127) / 128, std::min(rows, 65535), count);
+    mask_packed_batch_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const char *>(u0), reinterpret_cast<const char *>(u1), state,
+                                                  f32, bits, rows, w, pitch, plane_bytes, invert);
     return cudaGetLastError();
 }
 cudaError_t launch_checkerboard(double *u, const signed char *si, const signed char *sj, int row_lo, int rows, int w,
                                 int pitch, cudaStream_t s) {
-    dim3 grid((w + 255) / 256, rows);
+    dim3 grid((w + 255) / 256, std::min(rows, 65535));
     checkerboard_kernel<<<grid, 256, 0, s>>>(u, si, sj, row_lo, rows, w, pitch);
     return cudaGetLastError();
 }

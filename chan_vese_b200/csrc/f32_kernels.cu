@@ -430,17 +430,20 @@ __global__ void convert_f2d_kernel(const float *in, double *out, size_t n) {
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) out[q] = (double)in[q];
 }
 __global__ void mask_f32_kernel(const float *u, uint8_t *mask, int rows, int w, int pitch, int invert) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-    if (j >= w || i >= rows) return;
-    const size_t q = (size_t)i * pitch + j;
-    const uint8_t m = (u[q] > 0.0f) ? 1 : 0;  // separate(): float32(u) > 0 (src/main.cpp:395-400)
-    mask[q] = invert ? (uint8_t)(1 - m) : m;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= w) return;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y) {
+        const size_t q = (size_t)i * pitch + j;
+        const uint8_t m = (u[q] > 0.0f) ? 1 : 0;  // separate(): float32(u) > 0 (src/main.cpp:395-400)
+        mask[q] = invert ? (uint8_t)(1 - m) : m;
+    }
 }
 __global__ void checkerboard_f32_kernel(float *u, const signed char *si, const signed char *sj, int row_lo, int rows, int w,
                                         int pitch) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-    if (j >= w || i >= rows) return;
-    u[(size_t)(i + HALO) * pitch + j] = (float)((int)si[row_lo + i] * (int)sj[j]);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= w) return;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y)
+        u[(size_t)(i + HALO) * pitch + j] = (float)((int)si[row_lo + i] * (int)sj[j]);
 }
 __global__ void quantise_f32_kernel(const float *in, uint8_t *out, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -489,13 +492,13 @@ cudaError_t launch_convert_f2d(const float *in, double *out, size_t n, cudaStrea
     return cudaGetLastError();
 }
 cudaError_t launch_mask_f32(const float *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s) {
-    dim3 grid((w + 255) / 256, rows);
+    dim3 grid((w + 255) / 256, std::min(rows, 65535));
     mask_f32_kernel<<<grid, 256, 0, s>>>(u, mask, rows, w, pitch, invert);
     return cudaGetLastError();
 }
 cudaError_t launch_checkerboard_f32(float *u, const signed char *si, const signed char *sj, int row_lo, int rows, int w,
                                     int pitch, cudaStream_t s) {
-    dim3 grid((w + 255) / 256, rows);
+    dim3 grid((w + 255) / 256, std::min(rows, 65535));
     checkerboard_f32_kernel<<<grid, 256, 0, s>>>(u, si, sj, row_lo, rows, w, pitch);
     return cudaGetLastError();
 }

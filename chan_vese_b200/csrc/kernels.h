@@ -9,15 +9,30 @@
 
 namespace cvb {
 
-// Programmatic dependent launch of the step kernels (the next step's CTAs become resident during the tail of the running
-// one).  On for single-GPU jobs (small-image step latency -15..25 %); OFF for multi-rank row slabs, whose step kernels
-// end in a wait for the peers: CVB_PDL=0/1 overrides either default.
-inline bool use_pdl(bool multi_rank) {
+// Programmatic dependent launch of the step kernels: the next step's CTAs become resident during the tail of the
+// running one (they load the atan table, then block in griddepcontrol.wait until the running step has completed and
+// flushed).  On for every job, row slabs included: a slab's step kernel ends in a wait for the peers' sums, but every
+// CTA of that kernel is already resident or done when the dependent launch may start, and the peers wait only for
+// kernels that are queued BEFORE anything that waits for them (no cycle).  CVB_PDL=0 turns it off.
+inline bool use_pdl(bool /*multi_rank*/) {
     static const int env = [] {
         const char *e = getenv("CVB_PDL");
         return e ? (e[0] == '0' ? 0 : 1) : -1;
     }();
-    return env >= 0 ? env == 1 : !multi_rank;
+    return env != 0;
+}
+
+// cudaFuncAttributePreferredSharedMemoryCarveout applies per DEVICE: remember it per device ordinal, not per process.
+template <typename F>
+inline cudaError_t prefer_max_shared(F *func) {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
 }
 
 cudaError_t launch_csv_step(const CsvArgs &A, bool strict, cudaStream_t s);
@@ -28,6 +43,9 @@ cudaError_t launch_csv_finalize(const CsvArgs &A, int mode, cudaStream_t s);
 cudaError_t launch_delta_map(double *data, size_t n, double eps, cudaStream_t s);
 cudaError_t launch_mask(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s);
 cudaError_t launch_mask_packed(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, cudaStream_t s);
+// all images of a batch: bits = [count][rows][(w+7)/8]; each image's current buffer is picked from its own step counter
+cudaError_t launch_mask_packed_batch(const void *u0, const void *u1, const CsvState *state, int f32, uint8_t *bits, int count,
+                                     int rows, int w, int pitch, size_t plane_bytes, int invert, cudaStream_t s);
 // border halo rows := copies of the first / last image row (planes of any element size; row_bytes multiple of 16)
 cudaError_t launch_replicate_halo(void *base, size_t plane_bytes, size_t row_bytes, int nplanes, int rows, int top, int bottom,
                                   cudaStream_t s);

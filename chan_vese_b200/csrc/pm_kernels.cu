@@ -605,9 +605,7 @@ static cudaError_t launch_pm_t(const PmArgs &A, bool strict, cudaStream_t s) {
         pm_step_kernel<TIN, TOUT, true><<<grid, CTA_THREADS, 0, s>>>(A);
     else {
         // programmatic dependent launch (see csv_kernels.cu): step n+1's CTAs become resident during the tail of step n
-        static cudaError_t carve = cudaFuncSetAttribute(pm_step_kernel<TIN, TOUT, false>,
-                                                        cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                        (int)cudaSharedmemCarveoutMaxShared);
+        const cudaError_t carve = prefer_max_shared(pm_step_kernel<TIN, TOUT, false>);
         if (carve != cudaSuccess) return carve;
         if (!use_pdl(A.cv.nranks > 1)) {
             pm_step_kernel<TIN, TOUT, false><<<grid, CTA_THREADS, 0, s>>>(A);

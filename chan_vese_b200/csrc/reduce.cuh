@@ -86,7 +86,57 @@ __device__ __forceinline__ void csv_wait_fold(const CsvArgs &A) {
     if (lane == 0) b->finalized = prod;
 }
 
+// Whole warp: fixed-order sum of `nvec` partial vectors (NACC doubles each, contiguous at `base`): lane l adds vectors
+// l, l+32, l+64, ... in that order, then the lanes are combined with a fixed xor tree.  Four vectors per lane are
+// requested before the first addition (the additions keep their order; only the loads overlap), so a few hundred
+// vectors cost two or three L2 round trips instead of one per vector -- this sum sits in the tail of every step.
+template <int NCH, bool INIT>
+__device__ __forceinline__ void sum_vectors(const double *base, int nvec, int lane, double (&sum)[NACC]) {
+    constexpr int NP = NACC / 2;
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) sum[v] = 0.0;
+    auto pair_used = [](int q) { return slot_used<NCH, INIT>(2 * q) || slot_used<NCH, INIT>(2 * q + 1); };
+    int i = lane;
+    for (; i + 96 < nvec; i += 128) {
+        double2 t[4][NP];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+                if (pair_used(q)) t[k][q] = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)(i + 32 * k) * NACC) + q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                if (slot_used<NCH, INIT>(2 * q)) sum[2 * q] += t[k][q].x;
+                if (slot_used<NCH, INIT>(2 * q + 1)) sum[2 * q + 1] += t[k][q].y;
+            }
+    }
+    for (; i < nvec; i += 32) {
+        double2 t[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+            if (pair_used(q)) t[q] = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)i * NACC) + q);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            if (slot_used<NCH, INIT>(2 * q)) sum[2 * q] += t[q].x;
+            if (slot_used<NCH, INIT>(2 * q + 1)) sum[2 * q + 1] += t[q].y;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NACC; ++v)
+        if (slot_used<NCH, INIT>(v)) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum[v] += __shfl_xor_sync(0xffffffffu, sum[v], off);
+        }
+}
+
 // Whole warp, after the row loop.  acc holds per-lane sums.
+// Tree: CTA partial vectors -> (large jobs only: A.seg_level) one sum per row segment, added by the last CTA of the
+// segment -> one sum per reduction group, added by the last arrival of the group -> fold.  Every level adds its
+// inputs in index order, so the result depends on the tiling (tile rows, strips) and on nothing else: not on the
+// order in which CTAs finish, not on the number of GPUs.  The segment level keeps the chain that is exposed at the
+// end of a step short: without it the last group's finisher adds (segments per group) x (strips) vectors alone.
 template <int NCH, bool INIT>
 __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, int cb, int ncb, double (&acc)[NACC],
                                             int final_mode, bool pushed_rows = false) {
@@ -105,6 +155,7 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
     // local segments of this group
     const int sb = max(group_seg_begin(grp, G.nseg_global), G.seg0) - G.seg0;
     const int se = min(group_seg_begin(grp + 1, G.nseg_global), G.seg0 + G.nseg) - G.seg0;
+    const bool seg_level = A.seg_level != 0;
     int last = 0;
     if (pushed_rows) __threadfence_system();  // this warp stored boundary rows into a neighbour's halo
     __syncwarp();
@@ -113,29 +164,40 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
         for (int v = 0; v < NACC; ++v)
             if (slot_used<NCH, INIT>(v)) part[v] = acc[v];
         __threadfence();
-        const unsigned int old = atomicAdd(&st->group_ticket[grp], 1u);
-        last = (old == (unsigned int)((se - sb) * ncb) - 1u) ? 1 : 0;
+        if (seg_level) {
+            const unsigned int old = atomicAdd(&A.seg_ticket[(size_t)img * G.nseg + seg], 1u);
+            last = (old == (unsigned int)ncb - 1u) ? 1 : 0;
+        } else {
+            const unsigned int old = atomicAdd(&st->group_ticket[grp], 1u);
+            last = (old == (unsigned int)((se - sb) * ncb) - 1u) ? 1 : 0;
+        }
     }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
     __threadfence();
-    // ---- this warp finishes group grp: fixed-order sum of its partial vectors (lane l takes l, l+32, ...)
-    const int nvec = (se - sb) * ncb;
-    const double *base = A.partials + (((size_t)img * G.nseg + sb) * ncb) * NACC;
     double sum[NACC];
+    if (seg_level) {
+        // ---- this warp finishes segment seg: fixed-order sum of its strips' partial vectors
+        sum_vectors<NCH, INIT>(A.partials + (((size_t)img * G.nseg + seg) * ncb) * NACC, ncb, lane, sum);
+        if (lane == 0) {
+            double *ss = A.seg_sums + ((size_t)img * G.nseg + seg) * NACC;
 #pragma unroll
-    for (int v = 0; v < NACC; ++v) sum[v] = 0.0;
-    for (int i = lane; i < nvec; i += 32) {
-#pragma unroll
-        for (int v = 0; v < NACC; ++v)
-            if (slot_used<NCH, INIT>(v)) sum[v] += ld_cg(base + (size_t)i * NACC + v);
-    }
-#pragma unroll
-    for (int v = 0; v < NACC; ++v)
-        if (slot_used<NCH, INIT>(v)) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) sum[v] += __shfl_xor_sync(0xffffffffu, sum[v], off);
+            for (int v = 0; v < NACC; ++v)
+                if (slot_used<NCH, INIT>(v)) ss[v] = sum[v];
+            A.seg_ticket[(size_t)img * G.nseg + seg] = 0u;
+            __threadfence();
+            const unsigned int old = atomicAdd(&st->group_ticket[grp], 1u);
+            last = (old == (unsigned int)(se - sb) - 1u) ? 1 : 0;
         }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) return;
+        __threadfence();
+        // ---- ... and group grp: fixed-order sum of its segments' sums
+        sum_vectors<NCH, INIT>(A.seg_sums + ((size_t)img * G.nseg + sb) * NACC, se - sb, lane, sum);
+    } else {
+        // ---- this warp finishes group grp: fixed-order sum of its partial vectors
+        sum_vectors<NCH, INIT>(A.partials + (((size_t)img * G.nseg + sb) * ncb) * NACC, (se - sb) * ncb, lane, sum);
+    }
     const bool p2p = A.cv.p2p != 0;
     // multi-GPU: this reduction's number; its parity picks the group-sum buffer (double buffering against slow peers)
     const unsigned int prod = p2p ? ld_relaxed(&A.cv.box->produced) + 1u : 0u;
@@ -166,10 +228,11 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
     // slab session (count == 1): this rank's group sums go to every peer, then the arrival flags
     const size_t first = (size_t)A.group_lo * G.count * NACC;
     const int nval = (A.group_hi - A.group_lo) * G.count * NACC;
-    for (int p = 0; p < A.cv.nranks; ++p) {
-        if (p == A.cv.rank) continue;
-        double *dst = A.cv.peer_group[p] + (size_t)(prod & 1u) * NGROUPS * G.count * NACC + first;
-        for (int i = lane; i < nval; i += 32) dst[i] = ld_cg(gbase + first + i);
+    const size_t poff = (size_t)(prod & 1u) * NGROUPS * G.count * NACC + first;
+    for (int i = lane; i < nval; i += 32) {  // one load, nranks - 1 remote stores (posted writes over NVLink)
+        const double v = ld_cg(gbase + first + i);
+        for (int p = 0; p < A.cv.nranks; ++p)
+            if (p != A.cv.rank) A.cv.peer_group[p][poff + i] = v;
     }
     __threadfence_system();
     __syncwarp();

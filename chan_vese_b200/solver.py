@@ -111,6 +111,10 @@ class Context:
     def synchronize(self):
         self.check(self._lib.cvb_context_synchronize(self._h))
 
+    def trim(self):
+        """Free the device buffers the one-shot calls keep between calls of the same shape."""
+        self.check(self._lib.cvb_context_trim(self._h))
+
     # ---- multi-GPU: the id travels through the host application (torch.distributed, MPI, a file ...)
     def comm_create_id(self):
         buf = C.create_string_buffer(_ffi.COMM_ID_BYTES)
@@ -391,6 +395,25 @@ class Batch:
         m = np.empty((self.h, self.w), dtype=np.uint8)
         self.ctx.check(self._lib.cvb_batch_mask(self._h, int(index), int(bool(invert)), m.ctypes.data_as(_ffi.u8p)))
         return m
+
+    def masks_packed(self, invert=False, out=None):
+        """Bit-packed masks of all images (one launch, one copy): (count, h, (w+7)//8) uint8, numpy.packbits layout."""
+        wb = (self.w + 7) // 8
+        m = out if out is not None else np.empty((self.count, self.h, wb), dtype=np.uint8)
+        self.ctx.check(self._lib.cvb_batch_masks_packed(self._h, int(bool(invert)), m.ctypes.data_as(_ffi.u8p)))
+        return m
+
+    def upload_images_smooth(self, images, K, L, T):
+        """upload_images + perona_malik with the copies hidden behind the diffusion of the planes already there."""
+        arr = np.ascontiguousarray(images, dtype=np.uint8)
+        if arr.shape != (self.count, self.n, self.h, self.w):
+            raise ValueError("images shape %r, expected %r" % (arr.shape, (self.count, self.n, self.h, self.w)))
+        base = arr.ctypes.data
+        stride = self.h * self.w
+        ptrs = (_ffi.u8p * (self.count * self.n))(*[C.cast(base + p * stride, _ffi.u8p) for p in range(self.count * self.n)])
+        steps = C.c_int(0)
+        self.ctx.check(self._lib.cvb_batch_upload_images_smooth(self._h, ptrs, K, L, T, C.byref(steps)))
+        return steps.value
 
     def save_images(self):
         self.ctx.check(self._lib.cvb_batch_save_images(self._h))

@@ -92,6 +92,9 @@ cvb_status cvb_context_set_tile_rows(cvb_context *ctx, int rows);
 cvb_status cvb_context_get_stats(cvb_context *ctx, cvb_stats *out);
 cvb_status cvb_context_reset_stats(cvb_context *ctx);
 cvb_status cvb_context_synchronize(cvb_context *ctx);
+/* The one-shot calls below keep their device buffers (one whole-image session) in the context between calls of the
+ * same shape; this frees them (they are also freed by cvb_context_destroy and replaced when the shape changes). */
+cvb_status cvb_context_trim(cvb_context *ctx);
 /* Pinned host memory helpers (optional; any host pointer is accepted by the calls below). */
 cvb_status cvb_host_alloc(size_t bytes, void **out);
 void cvb_host_free(void *p);
@@ -106,8 +109,10 @@ cvb_status cvb_levelset_rect(int h, int w, int x, int y, int rw, int rh, double 
 /* InteractiveDataCirc::get_levelset, src/InteractiveDataCirc.cpp:18-25: one-pixel ring of 1 on 0. */
 cvb_status cvb_levelset_circ(int h, int w, int cx, int cy, int radius, double *u);
 
-/* Rows per tile the library would pick for a job of `count` h x w images cut into `nranks` row slabs (what
- * tile_rows = 0 means; nranks = 1 for whole images and batches). */
+/* Rows per tile the library would pick for a job of `count` h x w images (what tile_rows = 0 means).  The tiling
+ * fixes the order of the fused sums, so the choice does NOT depend on `nranks` (kept in the signature; any value
+ * >= 1 gives the same answer): a single image is tiled so that runs on 1, 2, 4 and 8 GPUs are all efficient and
+ * give bit-identical results. */
 int cvb_auto_tile_rows(int h, int w, int count, int nranks);
 /* Row slab [*row_lo, *row_hi) of rank `rank` of `nranks` (1, 2, 4, 8, 16 or 32) for an image of h rows cut
  * into tiles of tile_rows rows: slabs are unions of the library's 32 fixed reduction groups, so a slab run
@@ -182,7 +187,8 @@ cvb_status cvb_session_upload_image_smooth(cvb_session *s, const uint8_t *const 
  * save_image keeps a device copy of the current planes, restore_image brings it back (device to device). */
 cvb_status cvb_session_save_image(cvb_session *s);
 cvb_status cvb_session_restore_image(cvb_session *s);
-/* Frees the fp64 Perona-Malik scratch planes (they are re-allocated on demand). */
+/* Frees the fp64 Perona-Malik scratch planes (they are re-allocated on demand).  Not for multi-GPU slab sessions:
+ * their planes are mapped by the neighbouring ranks (CUDA IPC) for the session's lifetime -> CVB_ERR_STATE. */
 cvb_status cvb_session_release_scratch(cvb_session *s);
 
 /* ---- multi-GPU (one process per GPU; row slabs of one image) -------------------------------------- */
@@ -209,6 +215,8 @@ cvb_status cvb_batch_download_levelset(cvb_batch *b, int index, double *u);
 cvb_status cvb_batch_download_image(cvb_batch *b, int index, uint8_t *const *planes);
 cvb_status cvb_batch_mask(cvb_batch *b, int index, int invert, uint8_t *mask);
 cvb_status cvb_batch_mask_packed(cvb_batch *b, int index, int invert, uint8_t *bits);
+/* The packed masks of ALL images with one launch and one copy: bits = count * h * ((w+7)/8) bytes, image-major. */
+cvb_status cvb_batch_masks_packed(cvb_batch *b, int invert, uint8_t *bits);
 cvb_status cvb_batch_upload_images_smooth(cvb_batch *b, const uint8_t *const *planes, double K, double L, double T, int *steps);
 cvb_status cvb_batch_save_images(cvb_batch *b);
 cvb_status cvb_batch_restore_images(cvb_batch *b);

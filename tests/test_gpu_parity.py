@@ -347,6 +347,78 @@ def test_config4_full_size_windows(ctx):
     assert np.array_equal(m1, (u1.astype(np.float32) > 0).astype(np.uint8))
 
 
+@pytest.fixture(scope="module")
+def bench_scene():
+    """The bench's own 16384^2 RGB input (synth.hashed_scene_rows, BASELINE configs[3])."""
+    import os
+    return synth.hashed_scene_rows(16384, 16384, 0, 16384, threads=min(8, os.cpu_count() or 1))
+
+
+@pytest.mark.parametrize("tile_rows", [0, 186, 81])
+def test_config4_full_size_production_kernels(ctx, bench_scene, tile_rows):
+    """The kernels bench.py TIMES, at the geometry it times them: 16384^2 RGB, fast math (cp.async row rings), the
+    automatic tile length and the two of round 1 (186: one GPU, 81: eight).  PM 20 steps, then 6 CSV steps with given
+    region means -- both are local stencils then, so windows of the full-size result are compared with the oracle run on
+    the window plus a halo wider than the stencils reach (PM 20 steps: 40 pixels; CSV 6 steps: 12).  Windows sit on all
+    four image borders and corners, across tile seams (rows) and strip seams (columns) and in the interior.
+    Tolerances: PM planes |delta| <= 1 and >= 99.99 % equal (ties at x.5); level set rel-L2 <= 1e-9 and max-abs 1e-9 x
+    scale per window; mask identical."""
+    h = w = 16384
+    K, L, T, npm, ncsv = 10.0, 0.25, 5.0, 20, 6
+    c1, c2 = np.array([171.3, 139.9, 101.2]), np.array([93.7, 108.4, 125.6])
+    p_gpu, p_ref = cv.make_params(lambda1=[1.0, 0.5, 2.0]), co.params(lambda1=[1.0, 0.5, 2.0])
+    ctx.set_tile_rows(tile_rows)
+    try:
+        tr = tile_rows or cv.auto_tile_rows(h, w, 1, 1)
+        with cv.Session(ctx, 3, h, w) as s:
+            s.upload_image(bench_scene)
+            s.init_checkerboard()
+            assert s.perona_malik(K, L, T) == npm
+            pm = s.download_image()
+            for _ in range(ncsv):
+                s.csv_step(p_gpu, c1, c2)
+            u = s.download_levelset()
+            m = s.mask()
+    finally:
+        ctx.set_tile_rows(0)
+    u0 = cv.levelset_checkerboard(h, w)
+    seam = (h // 2 // tr) * tr          # a tile seam near the middle
+    strip = (w // 2 // 62) * 62         # a CSV strip seam; PM strips are 60 wide
+    pstrip = (w // 3 // 60) * 60
+    wins = [(0, 0), (0, w - 96), (h - 96, 0), (h - 96, w - 96), (0, 7000), (h - 96, 9000), (5000, 0), (11000, w - 96),
+            (seam - 48, strip - 48), (seam - 48, pstrip - 48), (tr - 40, 300), (h - tr - 50, 12000), (8111, 8222)]
+    HP, HC = 48, 16
+    worst_rel, pm_diff, pm_tot = 0.0, 0, 0
+    for (r0, c0) in wins:
+        # ---- PM: oracle on the raw scene window + 48
+        ra, rb, ca, cb = max(r0 - HP, 0), min(r0 + 96 + HP, h), max(c0 - HP, 0), min(c0 + 96 + HP, w)
+        ir = slice(r0 - ra, r0 - ra + 96)
+        ic = slice(c0 - ca, c0 - ca + 96)
+        for k in range(3):
+            ref = co.pm_evolve(np.ascontiguousarray(bench_scene[k][ra:rb, ca:cb]), K, L, npm)
+            q = np.clip(np.rint(ref), 0, 255).astype(np.int16)[ir, ic]
+            d = np.abs(q - pm[k][r0:r0 + 96, c0:c0 + 96].astype(np.int16))
+            assert d.max() <= 1, (tile_rows, r0, c0, k)
+            pm_diff += int((d != 0).sum())
+            pm_tot += d.size
+        # ---- CSV: oracle on the GPU's own PM planes (so a PM tie cannot leak into the level-set comparison) + 16
+        ra, rb, ca, cb = max(r0 - HC, 0), min(r0 + 96 + HC, h), max(c0 - HC, 0), min(c0 + 96 + HC, w)
+        ir = slice(r0 - ra, r0 - ra + 96)
+        ic = slice(c0 - ca, c0 - ca + 96)
+        sub = [np.ascontiguousarray(x[ra:rb, ca:cb]) for x in pm]
+        ur = np.ascontiguousarray(u0[ra:rb, ca:cb])
+        for _ in range(ncsv):
+            ur, _, _, _ = co.csv_step(sub, ur, p_ref, c1, c2)
+        a, b = u[r0:r0 + 96, c0:c0 + 96], ur[ir, ic]
+        rel = rel_l2(a, b)
+        worst_rel = max(worst_rel, rel)
+        assert rel <= 1e-9, (tile_rows, r0, c0, rel)
+        assert np.abs(a - b).max() <= 1e-9 * max(np.abs(b).max(), 1.0), (tile_rows, r0, c0)
+        assert np.array_equal(m[r0:r0 + 96, c0:c0 + 96], co.mask(b)), (tile_rows, r0, c0)
+    assert pm_diff <= 1e-4 * pm_tot, (pm_diff, pm_tot)
+    print("tile_rows=%d (%d): worst window rel-L2 %.2e, PM pixels off by one LSB %d of %d" % (tile_rows, tr, worst_rel, pm_diff, pm_tot))
+
+
 # ---- fp32 variant (reported separately: judged on the mask) ----------------------------------------------------------------
 def test_fp32_variant_config1(ctx, golden_c1):
     """CVB_PRECISION_F32 on BASELINE config 1: PM planes within 1 LSB, mask agreement >= 99.9 % with the fp64 reference

@@ -42,6 +42,7 @@ def main():
         which = ["C5"]
     stream = torch.cuda.Stream()
     ctx = cv.Context(local, stream=stream.cuda_stream)
+    ctx.set_tile_rows(int(os.environ.get("CVB_TILE_ROWS", "0")))
     res = {}
     for name in which:
         c = synth.CONFIGS[name]
