@@ -235,16 +235,17 @@ extern "C" cvb_status cvb_levelset_circ(int h, int w, int cx, int cy, int radius
 // 1.79 waves = 10 % idle, 79-row segments 2.91 waves = 3 %).  Small jobs keep >= 2 waves with at least 4 rows.
 static const int kSlots = 148 * 16;
 // min_tail > 0: lengths that leave a last segment of fewer than min_tail rows are not considered.
-static int wave_aware_rows(int rows_per_rank, long long ctas_per_seg, int min_tail = 0) {
+// slots: resident CTAs of the whole GPU; prime: rows' worth of work a CTA spends before its first output row.
+static int wave_aware_rows(int rows_per_rank, long long ctas_per_seg, int min_tail = 0, int slots = kSlots, double prime = 3.5) {
     int best = 0;
     double best_eff = -1.0;
     for (int r = 192; r >= 48; --r) {
         const int tail = rows_per_rank % r;
         if (tail != 0 && tail < min_tail) continue;
         const long long ctas = (long long)ceil_div(rows_per_rank, r) * ctas_per_seg;
-        const double waves = (double)ctas / kSlots;
+        const double waves = (double)ctas / slots;
         if (waves < 2.0) continue;
-        const double eff = waves / ceil(waves) * (1.0 - 3.5 / (r + 3.5));  // tail loss x priming overhead
+        const double eff = waves / ceil(waves) * (1.0 - prime / (r + prime));  // tail loss x priming overhead
         if (eff > best_eff + 1e-9) {
             best_eff = eff;
             best = r;
@@ -303,14 +304,14 @@ static int auto_seg_rows(int h, int w, int count, int /*nranks: deliberately unu
 // min_tail = HALO for the row slabs of a multi-rank run: the slab's last HALO rows should lie in ONE segment (they are
 // pushed to the neighbour by the CTAs of that segment; pm_push_boundary copes with a one-row last segment, but there is
 // no need to make one).  0 otherwise: whole images keep the plain choice.
-static int auto_pm_seg_rows(int rows, int w, int planes, int min_tail) {
-    const int ncb = ceil_div(w, PM_CB);
+static int auto_pm_seg_rows(int rows, int w, int planes, int min_tail, int strip = PM_CB, int slots = kSlots, double prime = 3.5) {
+    const int ncb = ceil_div(w, strip);
     auto tail_ok = [&](int s) { return rows % s == 0 || rows % s >= min_tail; };
-    const int r = wave_aware_rows(rows, (long long)planes * ncb, min_tail);
+    const int r = wave_aware_rows(rows, (long long)planes * ncb, min_tail, slots, prime);
     if (r > 0) return r;
     const int cands[] = {32, 16, 8, 4};
     for (int s : cands)
-        if ((long long)planes * ceil_div(rows, s) * ncb >= 2LL * kSlots && tail_ok(s)) return s;
+        if ((long long)planes * ceil_div(rows, s) * ncb >= 2LL * slots && tail_ok(s)) return s;
     for (int s : {4, 5, 6, 7})
         if (tail_ok(s)) return s;
     return 4;
@@ -555,8 +556,12 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     // PM has no reductions, so its segments need not follow the reduction groups: own wave-aware segment length
     g.pm_seg_rows = auto_pm_seg_rows(row_hi - row_lo, w, count * n, (slab && c->nranks > 1) ? HALO : 0);
     g.pm_nseg = ceil_div(row_hi - row_lo, g.pm_seg_rows);
+    // the fused two-step PM kernel: 56-column strips, 12 resident CTAs per SM, 4 priming rows more per segment
+    g.ncb_pm2 = ceil_div(w, PM2_CB);
+    g.pm2_seg_rows = auto_pm_seg_rows(row_hi - row_lo, w, count * n, (slab && c->nranks > 1) ? HALO : 0, PM2_CB, 148 * 12, 7.5);
+    g.pm2_nseg = ceil_div(row_hi - row_lo, g.pm2_seg_rows);
     g.plane_elems = (long long)g.rows_alloc * g.pitch;
-    if ((long long)count * n * std::max(g.nseg, g.pm_nseg) * std::max(g.ncb_csv, g.ncb_pm) > 0x7fffffffLL)
+    if ((long long)count * n * std::max(std::max(g.nseg, g.pm_nseg), g.pm2_nseg) * std::max(g.ncb_csv, g.ncb_pm2) > 0x7fffffffLL)
         return fail(c, CVB_ERR_INVALID_ARGUMENT, "job too large for one launch");
     // groups owned by this job
     j->ngroups_local = 0;
@@ -888,11 +893,19 @@ static cvb_status pm_run_planes(Job *j, int plane0, int np, double K, double L, 
     }
     uint8_t *img = j->d_img + poff;
     char *pm[2] = {reinterpret_cast<char *>(j->d_pm[0]) + poff * esz(j), reinterpret_cast<char *>(j->d_pm[1]) + poff * esz(j)};
-    for (int s = 1; s <= nsteps; ++s) {
-        const bool first = s == 1, last = s == nsteps && nsteps >= 2;
-        A.in = first ? (const void *)img : (const void *)pm[(s - 2) & 1];
-        A.out = last ? (void *)img : (void *)pm[(s - 1) & 1];
-        A.out_buf = last ? -1 : ((s - 1) & 1);
+    // Step 1 reads the uint8 image, step nsteps writes it; the fp64 -> fp64 steps in between run two per launch
+    // (pm2_step_kernel, temporal blocking), a left-over one alone.  CVB_PM_FUSE=0: one step per launch throughout.
+    const char *fuse_env = getenv("CVB_PM_FUSE");  // read per call: the bit-identity test switches it between two runs
+    const bool can_fuse = !(fuse_env && fuse_env[0] == '0') && !is_f32(j) && !strict;
+    int cur = -1;  // PM state buffer holding the newest fp64 planes (-1: the uint8 image)
+    for (int s = 1; s <= nsteps;) {
+        const bool first = s == 1;
+        const bool fused = can_fuse && !first && s + 2 <= nsteps;  // steps s, s+1 are both fp64 -> fp64
+        const bool last = !fused && s == nsteps && nsteps >= 2;
+        const int nxt = cur < 0 ? 0 : cur ^ 1;
+        A.in = first ? (const void *)img : (const void *)pm[cur];
+        A.out = last ? (void *)img : (void *)pm[nxt];
+        A.out_buf = last ? -1 : nxt;
         if (j->p2p) {
             // boundary rows travel inside the kernel (stores into the neighbours' halos + a flag); before a launch
             // that READS pushed rows, one warp waits for both neighbours' flags of the previous launch
@@ -904,14 +917,18 @@ static cvb_status pm_run_planes(Job *j, int plane0, int np, double K, double L, 
         }
         if (is_f32(j))
             CU(c, launch_pm_step_f32(A, first, last, c->stream));
+        else if (fused)
+            CU(c, launch_pm2_step(A, c->stream));
         else
             CU(c, launch_pm_step(A, first, last, strict, c->stream));
         c->stats.kernel_launches += 1;
         c->stats.pm_step_launches += 1;
         if (last)
             TRY(exchange_halo(j, img, 1, np));
-        else if (s < nsteps && !j->p2p)
-            TRY(exchange_halo(j, pm[(s - 1) & 1], sizeof(double), np));
+        else if (s + (fused ? 1 : 0) < nsteps && !j->p2p)
+            TRY(exchange_halo(j, pm[nxt], sizeof(double), np));
+        if (!last) cur = nxt;
+        s += fused ? 2 : 1;
     }
     if (nsteps == 1) {  // u8 -> fp64 -> u8: the single step cannot write the plane it reads
         if (is_f32(j))

@@ -17,7 +17,7 @@
 
 namespace cvb {
 
-constexpr int HALO = 2;            // halo rows above and below a slab (PM needs 2/2, CSV 2/1)
+constexpr int HALO = 4;            // halo rows above and below a slab (two fused PM steps need 4/4, one 2/2, CSV 2/1)
 constexpr int TAIL_ROWS = 12;      // rows of slack after the last plane of the u / image buffers (CSV register + L2 prefetch
                                    // run unconditionally up to CSV_PF + 1 rows past the end of a segment)
 constexpr int WARPS_PER_CTA = 1;   // a CTA = one warp = one column strip of one row segment: no block barriers,
@@ -28,6 +28,7 @@ constexpr int CSV_STRIP_OWN = 62;  // lane 0 is a halo lane (it supplies nx of t
 constexpr int PM_STRIP_OWN = 60;   // lanes 0 and 31 are halo lanes (radius-2 stencil)
 constexpr int CSV_CB = WARPS_PER_CTA * CSV_STRIP_OWN;  // columns per CTA
 constexpr int PM_CB = WARPS_PER_CTA * PM_STRIP_OWN;    // columns per CTA
+constexpr int PM2_CB = 56;         // fused two-step PM: lanes 0, 1, 30, 31 are halo lanes (radius-4 stencil)
 constexpr int MAX_CH = 3;
 // Accumulator slots of the fused reductions.  a(u) = atan(u/eps)/pi = H(u) - 1/2 (src/main.cpp:188-194):
 //   [0] sum a   [1..3] sum I_k*a   [4] sum du^2 (step) or sum mean_k(I)^2 (init)   [5..7] sum I_k (init)
@@ -49,6 +50,7 @@ struct Geom {
     int nseg_global;     // segments of the whole image
     int ncb_csv, ncb_pm; // column blocks (CTAs per segment)
     int pm_seg_rows, pm_nseg;  // PM segments: [row_lo + s*pm_seg_rows, ...) (PM has no reduction groups to follow)
+    int ncb_pm2, pm2_seg_rows, pm2_nseg;  // tiling of the fused two-step PM kernel (56-column strips)
     long long plane_elems;  // rows_alloc * pitch
 };
 

@@ -81,14 +81,12 @@ __device__ __noinline__ bool push_boundary_rows(const CsvArgs &A, const double *
 __device__ __noinline__ void replicate_border_rows(double *uout, const Geom &G, int ra, int rb, int a) {
     if (ra == 0) {
         const double2 v = __ldcg(reinterpret_cast<const double2 *>(uout + (size_t)(0 - G.row_lo + HALO) * G.pitch + a));
-        *reinterpret_cast<double2 *>(uout + (size_t)0 * G.pitch + a) = v;
-        *reinterpret_cast<double2 *>(uout + (size_t)1 * G.pitch + a) = v;
+        for (int k = 0; k < HALO; ++k) *reinterpret_cast<double2 *>(uout + (size_t)k * G.pitch + a) = v;
     }
     if (rb == G.h) {
         const size_t last = (size_t)(G.h - 1 - G.row_lo + HALO);
         const double2 v = __ldcg(reinterpret_cast<const double2 *>(uout + last * G.pitch + a));
-        *reinterpret_cast<double2 *>(uout + (last + 1) * G.pitch + a) = v;
-        *reinterpret_cast<double2 *>(uout + (last + 2) * G.pitch + a) = v;
+        for (int k = 1; k <= HALO; ++k) *reinterpret_cast<double2 *>(uout + (last + k) * G.pitch + a) = v;
     }
 }
 
@@ -765,21 +763,19 @@ __global__ void checkerboard_kernel(double *u, const signed char *si, const sign
         u[(size_t)(i + HALO) * pitch + j] = (double)((int)si[row_lo + i] * (int)sj[j]);
 }
 
-// Fill the border halo rows of freshly written planes (upload, initialisers): rows -2,-1 := row 0 when the job owns
-// the image top, rows h, h+1 := row h-1 when it owns the bottom.  One thread per 16 bytes of a row.
+// Fill the border halo rows of freshly written planes (upload, initialisers): the HALO rows above row 0 := row 0 when the job
+// owns the image top, the HALO rows below row h-1 := row h-1 when it owns the bottom.  One thread per 16 bytes of a row.
 __global__ void replicate_halo_kernel(uint8_t *base, size_t plane_bytes, size_t row_bytes, int rows, int top, int bottom) {
     uint8_t *pl = base + (size_t)blockIdx.y * plane_bytes;
     const size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (x >= row_bytes) return;
     if (top) {
         const uint4 v = *reinterpret_cast<const uint4 *>(pl + (size_t)HALO * row_bytes + x);
-        *reinterpret_cast<uint4 *>(pl + x) = v;
-        *reinterpret_cast<uint4 *>(pl + row_bytes + x) = v;
+        for (int k = 0; k < HALO; ++k) *reinterpret_cast<uint4 *>(pl + (size_t)k * row_bytes + x) = v;
     }
     if (bottom) {
         const uint4 v = *reinterpret_cast<const uint4 *>(pl + (size_t)(HALO + rows - 1) * row_bytes + x);
-        *reinterpret_cast<uint4 *>(pl + (size_t)(HALO + rows) * row_bytes + x) = v;
-        *reinterpret_cast<uint4 *>(pl + (size_t)(HALO + rows + 1) * row_bytes + x) = v;
+        for (int k = 0; k < HALO; ++k) *reinterpret_cast<uint4 *>(pl + (size_t)(HALO + rows + k) * row_bytes + x) = v;
     }
 }
 cudaError_t launch_replicate_halo(void *base, size_t plane_bytes, size_t row_bytes, int nplanes, int rows, int top, int bottom,

@@ -173,14 +173,12 @@ __device__ __forceinline__ void csv_rows_f32(const float *__restrict__ uin, floa
 __device__ __noinline__ void replicate_border_rows_f32(float *uout, const Geom &G, int ra, int rb, int a) {
     if (ra == 0) {
         const float2 v = __ldcg(reinterpret_cast<const float2 *>(uout + (size_t)(0 - G.row_lo + HALO) * G.pitch + a));
-        *reinterpret_cast<float2 *>(uout + (size_t)0 * G.pitch + a) = v;
-        *reinterpret_cast<float2 *>(uout + (size_t)1 * G.pitch + a) = v;
+        for (int k = 0; k < HALO; ++k) *reinterpret_cast<float2 *>(uout + (size_t)k * G.pitch + a) = v;
     }
     if (rb == G.h) {
         const size_t last = (size_t)(G.h - 1 - G.row_lo + HALO);
         const float2 v = __ldcg(reinterpret_cast<const float2 *>(uout + last * G.pitch + a));
-        *reinterpret_cast<float2 *>(uout + (last + 1) * G.pitch + a) = v;
-        *reinterpret_cast<float2 *>(uout + (last + 2) * G.pitch + a) = v;
+        for (int k = 1; k <= HALO; ++k) *reinterpret_cast<float2 *>(uout + (last + k) * G.pitch + a) = v;
     }
 }
 

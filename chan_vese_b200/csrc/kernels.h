@@ -54,6 +54,8 @@ cudaError_t launch_checkerboard(double *u, const signed char *si, const signed c
 
 // in_u8 / out_u8: the first step reads the uint8 image, the last one writes it (fused quantisation)
 cudaError_t launch_pm_step(const PmArgs &A, bool in_u8, bool out_u8, bool strict, cudaStream_t s);
+// two diffusion steps fused into one pass (temporal blocking), fp64 planes in and out; tiling g.ncb_pm2 / pm2_seg_rows
+cudaError_t launch_pm2_step(const PmArgs &A, cudaStream_t s);
 // P2P slab runs: one warp polls the neighbours' flags between two PM launches
 cudaError_t launch_pm_wait(CommBox *box, unsigned int need, int has_up, int has_dn, cudaStream_t s);
 cudaError_t launch_pm_quantise(const double *in, uint8_t *out, size_t n, cudaStream_t s);

@@ -371,6 +371,225 @@ __device__ __forceinline__ void pm_rows_ring(const double *__restrict__ in, TOUT
     while (r < n) row((unsigned int)((r + 4) % PM_RING_NS) * S);
 }
 
+// ---- TWO diffusion steps per launch (temporal blocking) --------------------------------------------------------
+// The PM step is HBM-bound (16 B per channel-pixel against ~43 FP64 operations); two consecutive steps fused into one
+// pass read and write every plane once instead of twice.  A warp marches two stencils down its strip, the second one
+// two rows behind the first:
+//   stage A = pm_rows_ring, operation for operation: I rows from the cp.async input ring -> J = PM(I), rows ra-2 .. rb+1;
+//             instead of going to HBM a J row is put into a small shared-memory ring (its east / west neighbours come
+//             back from there, as those of I come from the input ring);
+//   stage B = the same arithmetic on the J rows -> out = PM(J), rows ra .. rb-1.
+// The stencil of two steps has radius 4: lanes 0, 1, 30 and 31 are halo lanes (a strip owns 56 columns), stage A needs
+// I rows ra-4 .. rb+3 (HALO = 4 rows around every slab).  Bit-identical to two single launches: every J value is the
+// double the first launch would have stored, every operation of stage B the one the second launch would execute.
+// Image borders: g = 1 on the border rows and columns and zero flux across them in BOTH stages (:516, :527-530).  The
+// J rows above row 0 / below row h-1 that stage A makes out of the replicated halo rows are NOT copies of J(0) / J(h-1),
+// as the clamped neighbours of the second step require; stage B therefore takes the flux across the top border as
+// zero and substitutes J(h-1) for the rows below the image (BROWS instantiation only).
+constexpr int PM2_STRIP_OWN = 56;
+constexpr int PM2_JNS = 6;  // J ring slots: the prologue of stage B needs 4 rows; 6 keeps every slot offset constant
+constexpr int PM2_SMEM = (PM_RING_NS + PM2_JNS) * PM_RING_SLOT;
+#ifndef PM2_MIN_CTAS
+#define PM2_MIN_CTAS 12
+#endif
+
+template <bool EDGE, bool BROWS>
+__device__ __forceinline__ void pm2_rows_ring(const double *__restrict__ in, double *__restrict__ out, const Geom &G,
+                                              unsigned char *ring, unsigned char *jring, int ra, int rb, int a, int lane,
+                                              double inv_k2, double lq) {
+    const int w = G.w, h = G.h;
+    const bool colok = !EDGE || (a >= 0 && a < G.pitch);
+    const bool bc0 = EDGE && (a == 0 || a == w - 1), bc1 = EDGE && a + 1 == w - 1;  // border columns
+    const bool nofxw = EDGE && a == 0, nofx0 = EDGE && a == w - 1;
+    const bool own = lane >= 2 && lane <= 29;
+    auto fixg = [&](double2 &g) {
+        if (EDGE) {
+            g.x = bc0 ? 1.0 : g.x;
+            g.y = bc1 ? 1.0 : g.y;
+        }
+    };
+    const size_t pitch = (size_t)G.pitch;
+    const double *pin = in + (size_t)(ra - 4 - G.row_lo + HALO) * pitch + a;  // row ra-4 = ring row 0
+    double *po = out + (size_t)(ra - G.row_lo + HALO) * pitch + a;            // row ra
+    const int n = rb - ra;
+    const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring) + 16 + 16 * lane;
+    const unsigned char *my = ring + 16 + 16 * lane;  // + slot: own chunk; west neighbour at -8, east at +16
+    unsigned char *jmy = jring + 16 + 16 * lane;
+
+    auto issue = [&](unsigned int slot_off) {  // the next ring row
+        if (colok) cp_async16(ring_s + slot_off, pin);
+        pin += pitch;
+    };
+    struct Row {
+        double2 X;
+        double Wn, E2;
+    };
+    auto fetch = [&](const unsigned char *base, unsigned int slot_off) {
+        Row r;
+        r.X = *reinterpret_cast<const double2 *>(base + slot_off);
+        r.Wn = *reinterpret_cast<const double *>(base + slot_off - 8);
+        r.E2 = *reinterpret_cast<const double *>(base + slot_off + 16);
+        return r;
+    };
+    auto sobel_rows = [&](const Row &r, double2 &rd, double2 &rs) {  // separable Sobel, row pass
+        rd.x = r.X.y - r.Wn;
+        rs.x = fma(2.0, r.X.x, r.Wn) + r.X.y;
+        rd.y = r.E2 - r.X.x;
+        rs.y = fma(2.0, r.X.y, r.X.x) + r.E2;
+    };
+    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, gy * gy), inv_k2, 1.0)); };  // :518-521
+
+    // what one diffusion step carries from row to row (the locals of pm_rows_ring)
+    struct Carry {
+        double2 IC, IS;    // rows i, i+1
+        double ICe, ISe;   // their east neighbours (column a+2)
+        double2 P;         // rd(i) + 2 rd(i+1)
+        double2 rdB;       // rd(i+1)
+        double2 rsA, rsB;  // rs(i), rs(i+1)
+        double2 gC;        // g(i)
+        double fy0, fy1;   // Fy(i-1/2)
+    };
+    // rows i-2 .. i+1 give g(i-1), g(i) and the flux Fy(i-1/2); i = first output row of the stage
+    auto prologue = [&](Carry &c, const Row &Q0, const Row &Q1, const Row &Q2, const Row &Q3, int i, bool zero_top_flux) {
+        double2 rd0, rs0, rd1, rs1, rd2, rs2, rd3, rs3;
+        sobel_rows(Q0, rd0, rs0);
+        sobel_rows(Q1, rd1, rs1);
+        sobel_rows(Q2, rd2, rs2);
+        sobel_rows(Q3, rd3, rs3);
+        double2 gP;
+        gP.x = edge((rd0.x + 2.0 * rd1.x) + rd2.x, rs2.x - rs0.x);
+        gP.y = edge((rd0.y + 2.0 * rd1.y) + rd2.y, rs2.y - rs0.y);
+        c.gC.x = edge((rd1.x + 2.0 * rd2.x) + rd3.x, rs3.x - rs1.x);
+        c.gC.y = edge((rd1.y + 2.0 * rd2.y) + rd3.y, rs3.y - rs1.y);
+        if (i == 0 || i == h - 1) c.gC = make_double2(1.0, 1.0);  // g = 1 on the image border rows (:516)
+        fixg(gP);
+        fixg(c.gC);
+        c.fy0 = (gP.x + c.gC.x) * (Q2.X.x - Q1.X.x);
+        c.fy1 = (gP.y + c.gC.y) * (Q2.X.y - Q1.X.y);
+        if (BROWS && zero_top_flux && i == 0) c.fy0 = c.fy1 = 0.0;  // stage B: J(-1) := J(0)
+        c.IC = Q2.X;
+        c.IS = Q3.X;
+        c.ICe = Q2.E2;
+        c.ISe = Q3.E2;
+        c.P = make_double2(fma(2.0, rd3.x, rd2.x), fma(2.0, rd3.y, rd2.y));
+        c.rdB = rd3;
+        c.rsA = rs2;
+        c.rsB = rs3;
+    };
+    // one output row i of a stage: Q = row i+2
+    auto step = [&](Carry &c, const Row &Q, int i, double &o0, double &o1) {
+        double2 rdC, rsC;
+        sobel_rows(Q, rdC, rsC);
+        double2 gS;
+        gS.x = edge(c.P.x + rdC.x, rsC.x - c.rsA.x);
+        gS.y = edge(c.P.y + rdC.y, rsC.y - c.rsA.y);
+        if (BROWS && (i + 1 == 0 || i + 1 == h - 1)) gS = make_double2(1.0, 1.0);  // g = 1 on the border rows (:516)
+        fixg(gS);
+        const double fs0 = (c.gC.x + gS.x) * (c.IS.x - c.IC.x), fs1 = (c.gC.y + gS.y) * (c.IS.y - c.IC.y);  // Fy(i+1/2)
+        const double ge = __shfl_down_sync(0xffffffffu, c.gC.x, 1);
+        double fx0 = (c.gC.x + c.gC.y) * (c.IC.y - c.IC.x);  // Fx(a+1/2)
+        double fx1 = (c.gC.y + ge) * (c.ICe - c.IC.y);       // Fx(a+3/2)
+        if (EDGE) {
+            fx0 = nofx0 ? 0.0 : fx0;
+            fx1 = bc1 ? 0.0 : fx1;
+        }
+        double fxw = __shfl_up_sync(0xffffffffu, fx1, 1);  // Fx(a-1/2)
+        if (EDGE) fxw = nofxw ? 0.0 : fxw;
+        o0 = fma((fs0 - c.fy0) + (fx0 - fxw), lq, c.IC.x);
+        o1 = fma((fs1 - c.fy1) + (fx1 - fx0), lq, c.IC.y);
+        c.fy0 = fs0;
+        c.fy1 = fs1;
+        c.P.x = fma(2.0, rdC.x, c.rdB.x);
+        c.P.y = fma(2.0, rdC.y, c.rdB.y);
+        c.rdB = rdC;
+        c.rsA = c.rsB;
+        c.rsB = rsC;
+        c.IC = c.IS;
+        c.ICe = c.ISe;
+        c.IS = Q.X;
+        c.ISe = Q.E2;
+        c.gC = gS;
+    };
+
+    constexpr unsigned int S = PM_RING_SLOT, H = 6 * PM_RING_SLOT;
+    // ring rows 0 .. NS-1, two per group
+#pragma unroll
+    for (int k = 0; k < PM_RING_NS; k += 2) {
+        issue(k * S);
+        issue((k + 1) * S);
+        cp_async_commit();
+    }
+    cp_async_wait<PM_RING_NS / 2 - 2>();  // ring rows 0..3 have landed
+    __syncwarp();
+    Carry A, B;
+    prologue(A, fetch(my, 0), fetch(my, S), fetch(my, 2 * S), fetch(my, 3 * S), ra - 2, false);
+    int rowA = ra - 2;  // J row stage A produces next; it consumes ring row (rowA - ra) + 6
+    // stage A alone: J rows ra-2 .. ra+1 into J slots 0..3 (ring rows 4..7; refill ring slots 0..3 with rows 12..15)
+    auto a_row = [&](unsigned int s_x, unsigned int s_j) {
+        double o0, o1;
+        step(A, fetch(my, s_x), rowA, o0, o1);
+        *reinterpret_cast<double2 *>(jmy + s_j) = make_double2(o0, o1);
+        ++rowA;
+    };
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+        issue(k * S);
+        issue((k + 1) * S);
+        cp_async_commit();
+        cp_async_wait<PM_RING_NS / 2 - 2>();
+        __syncwarp();
+        a_row((4 + k) * S, k * S);
+        a_row((5 + k) * S, (k + 1) * S);
+    }
+    __syncwarp();
+    {
+        const Row J2 = fetch(jmy, 2 * S);
+        Row J3 = fetch(jmy, 3 * S);
+        if (BROWS && ra + 1 >= h) J3.X = J2.X;  // one-row image: J(1) := J(0)
+        prologue(B, fetch(jmy, 0), fetch(jmy, S), J2, J3, ra, true);
+    }
+    int r = 0;
+    // one output row ra + r: stage A makes J row ra+2+r from ring row r+8 (slot s_x) into J slot s_j, stage B consumes it
+    auto row = [&](unsigned int s_x, unsigned int s_j) {
+        a_row(s_x, s_j);
+        __syncwarp();
+        Row Q = fetch(jmy, s_j);
+        if (BROWS && ra + r + 2 >= h) Q.X = B.IS;  // below the image: J(h), J(h+1) := J(h-1) (clamped neighbours, :527-528)
+        double o0, o1;
+        step(B, Q, ra + r, o0, o1);
+        if (EDGE) {
+            if (own && a < w) pm_store(po, o0, o1, a + 1 < w);
+        } else if (own) {
+            pm_store(po, o0, o1, true);
+        }
+        po += pitch;
+        ++r;
+    };
+    // two rows: refill the two ring slots freed longest ago (ring rows r+4, r+5 -> r+16, r+17), wait for ring rows r+8, r+9
+    auto pair = [&](unsigned int s_w0, unsigned int s_x0, unsigned int s_j0) {
+        issue(s_w0);
+        issue(s_w0 + S);
+        cp_async_commit();
+        cp_async_wait<PM_RING_NS / 2 - 2>();
+        __syncwarp();
+        row(s_x0, s_j0);
+        row(s_x0 + S, s_j0 + S);
+    };
+    unsigned int tog = 0;  // (r mod 12) slots: 0 or 6
+#pragma unroll 1
+    while (r + 6 <= n) {
+        const unsigned int t2 = H - tog;
+        pair(tog + 4 * S, t2 + 2 * S, 4 * S);
+        pair(t2, t2 + 4 * S, 0);
+        pair(t2 + 2 * S, tog, 2 * S);
+        tog = t2;
+    }
+    cp_async_wait<0>();  // the rows of the tail (<= 5) have all been requested
+    __syncwarp();
+#pragma unroll 1
+    while (r < n) row((unsigned int)((r + 8) % PM_RING_NS) * S, (unsigned int)((r + 4) % PM2_JNS) * S);
+}
+
 template <typename TIN, typename TOUT, bool STRICT>
 __device__ __forceinline__ void pm_rows_generic(const TIN *__restrict__ in, TOUT *__restrict__ out, const Geom &G, int ra,
                                                 int rb, int a, int lane, bool colok, double K, double L, double inv_k2,
@@ -482,12 +701,14 @@ __device__ __noinline__ void pm_replicate_border(TOUT *out, const Geom &G, int r
 // P2P multi-GPU: the slab's first / last HALO rows are the neighbours' halo rows.  Read back what this warp just
 // wrote and store it into the neighbour's output buffer; the LAST boundary CTA of the launch then raises the
 // neighbour's flag (st.release.sys after system fences), which pm_wait_kernel polls before the next launch.
+// lane_lo .. lane_hi: the lanes that own columns; ncb / seg_rows / nseg: the tiling of the launching kernel.
 template <typename TOUT>
-__device__ __noinline__ void pm_push_boundary(const PmArgs &A, const TOUT *out, int plane, int ra, int rb, int a, int lane) {
+__device__ __noinline__ void pm_push_boundary(const PmArgs &A, const TOUT *out, int plane, int ra, int rb, int a, int lane,
+                                              int lane_lo, int lane_hi, int ncb, int seg_rows, int nseg) {
     const Geom &G = A.g;
     const bool top = ra < G.row_lo + HALO && A.cv.rank > 0, bot = rb > G.row_hi - HALO && A.cv.rank < A.cv.nranks - 1;
     if (!top && !bot) return;
-    if (sizeof(TOUT) == 8 && A.out_buf >= 0 && lane >= 1 && lane <= 30 && a < G.w) {
+    if (sizeof(TOUT) == 8 && A.out_buf >= 0 && lane >= lane_lo && lane <= lane_hi && a < G.w) {
         const double *o = reinterpret_cast<const double *>(out);
         for (int i = ra; i < rb; ++i) {
             const bool t = top && i < G.row_lo + HALO, b = bot && i >= G.row_hi - HALO;
@@ -512,9 +733,9 @@ __device__ __noinline__ void pm_push_boundary(const PmArgs &A, const TOUT *out, 
     if (lane == 0) {
         // boundary CTAs per side: the first HALO rows lie in one segment (segments have >= 4 rows), the last HALO rows
         // in two when the slab's last segment is a single row
-        const unsigned int nb = (unsigned int)(G.ncb_pm * G.count * G.nch);
-        const int last_rows = (G.row_hi - G.row_lo) - (G.pm_nseg - 1) * G.pm_seg_rows;
-        const unsigned int nb_dn = (G.pm_nseg > 1 && last_rows < HALO) ? 2u * nb : nb;
+        const unsigned int nb = (unsigned int)(ncb * G.count * G.nch);
+        const int last_rows = (G.row_hi - G.row_lo) - (nseg - 1) * seg_rows;
+        const unsigned int nb_dn = (nseg > 1 && last_rows < HALO) ? 2u * nb : nb;
         if (top) {
             __threadfence();
             if (atomicAdd(&A.cv.box->pm_ticket_up, 1u) == nb - 1u) {
@@ -589,8 +810,47 @@ __global__ void __launch_bounds__(CTA_THREADS, PM_MIN_CTAS) pm_step_kernel(const
         pm_rows_generic<TIN, TOUT, STRICT>(in, out, G, ra, rb, a, lane, colok, K, L, inv_k2, lq);
     }
     if ((ra == 0 || rb == h) && lane >= 1 && lane <= 30 && a < w) pm_replicate_border<TOUT>(out, G, ra, rb, a);
-    if (A.cv.p2p) pm_push_boundary<TOUT>(A, out, plane, ra, rb, a, lane);
+    if (A.cv.p2p) pm_push_boundary<TOUT>(A, out, plane, ra, rb, a, lane, 1, 30, G.ncb_pm, G.pm_seg_rows, G.pm_nseg);
 }
+
+template <int DUMMY>
+__global__ void __launch_bounds__(CTA_THREADS, PM2_MIN_CTAS) pm2_step_kernel(const __grid_constant__ PmArgs A) {
+    const Geom &G = A.g;
+    const int lane = threadIdx.x;
+    int bid = blockIdx.x;
+    const int cb = bid % G.ncb_pm2;
+    bid /= G.ncb_pm2;
+    const int seg = bid % G.pm2_nseg;
+    const int plane = bid / G.pm2_nseg;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    const double *__restrict__ in = reinterpret_cast<const double *>(A.in) + (size_t)plane * G.plane_elems;
+    double *__restrict__ out = reinterpret_cast<double *>(A.out) + (size_t)plane * G.plane_elems;
+    const int ra = G.row_lo + seg * G.pm2_seg_rows;
+    const int rb = min(ra + G.pm2_seg_rows, G.row_hi);
+    const int cs = cb * PM2_STRIP_OWN;
+    if (cs >= G.w) return;
+    const int a = cs - 4 + 2 * lane;
+    const int w = G.w, h = G.h;
+    const double inv_k2 = A.inv_k2, lq = A.L * 0.25;
+    const bool interior = cb >= 1 && (cb + 1) * PM2_STRIP_OWN + 4 <= w;
+    const bool brows = ra <= 2 || rb + 2 >= h;  // a stage meets row 0 or row h-1 inside this segment
+    __shared__ __align__(16) unsigned char s_ring[PM2_SMEM];
+    unsigned char *jring = s_ring + PM_RING_NS * PM_RING_SLOT;
+    if (brows) {
+        if (interior)
+            pm2_rows_ring<false, true>(in, out, G, s_ring, jring, ra, rb, a, lane, inv_k2, lq);
+        else
+            pm2_rows_ring<true, true>(in, out, G, s_ring, jring, ra, rb, a, lane, inv_k2, lq);
+    } else if (interior) {
+        pm2_rows_ring<false, false>(in, out, G, s_ring, jring, ra, rb, a, lane, inv_k2, lq);
+    } else {
+        pm2_rows_ring<true, false>(in, out, G, s_ring, jring, ra, rb, a, lane, inv_k2, lq);
+    }
+    if ((ra == 0 || rb == h) && lane >= 2 && lane <= 29 && a < w) pm_replicate_border<double>(out, G, ra, rb, a);
+    if (A.cv.p2p) pm_push_boundary<double>(A, out, plane, ra, rb, a, lane, 2, 29, G.ncb_pm2, G.pm2_seg_rows, G.pm2_nseg);
+}
+
 
 __global__ void pm_quantise_kernel(const double *in, uint8_t *out, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -631,6 +891,29 @@ cudaError_t launch_pm_step(const PmArgs &A, bool in_u8, bool out_u8, bool strict
     if (in_u8) return launch_pm_t<uint8_t, double>(A, strict, s);
     if (out_u8) return launch_pm_t<double, uint8_t>(A, strict, s);
     return launch_pm_t<double, double>(A, strict, s);
+}
+
+// two fused steps, fp64 planes in and out
+cudaError_t launch_pm2_step(const PmArgs &A, cudaStream_t s) {
+    const Geom &G = A.g;
+    const unsigned int grid = (unsigned int)((size_t)G.count * G.nch * G.pm2_nseg * G.ncb_pm2);
+    const cudaError_t carve = prefer_max_shared(pm2_step_kernel<0>);
+    if (carve != cudaSuccess) return carve;
+    if (!use_pdl(A.cv.nranks > 1)) {
+        pm2_step_kernel<0><<<grid, CTA_THREADS, 0, s>>>(A);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(CTA_THREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, pm2_step_kernel<0>, A);
 }
 
 cudaError_t launch_pm_wait(CommBox *box, unsigned int need, int has_up, int has_dn, cudaStream_t s) {

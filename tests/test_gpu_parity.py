@@ -555,3 +555,56 @@ def test_random_shapes_against_oracle(ctx):
         assert npm == nr
         d = np.abs(np.stack(out).astype(int) - np.stack(refp).astype(int))
         assert d.max() <= 1 and (d == 0).mean() >= 0.995, (case, h, w, n, d.max(), (d == 0).mean())
+
+
+# ---- Perona-Malik temporal blocking: two steps per launch must equal two launches, bit for bit --------------------
+def _pm_both_ways(ctx, img, K, L, T, batch=None):
+    import os
+    out = []
+    for fuse in ("0", "1"):
+        os.environ["CVB_PM_FUSE"] = fuse
+        try:
+            if batch is None:
+                planes, n = ctx.perona_malik(img, K, L, T)
+            else:
+                with cv.Batch(ctx, *batch) as b:
+                    b.upload_images(img)
+                    n = b.perona_malik(K, L, T)
+                    planes = [p for m in range(batch[0]) for p in b.download_image(m)]
+        finally:
+            os.environ.pop("CVB_PM_FUSE", None)
+        out.append((planes, n))
+    return out
+
+
+@pytest.mark.parametrize("shape", [(1, 70), (2, 9), (3, 1), (5, 57), (11, 56), (64, 113), (97, 300), (250, 370), (513, 1025)])
+@pytest.mark.parametrize("nsteps", [3, 4, 5, 8, 11])
+def test_pm_two_steps_per_launch_bit_identical(ctx, shape, nsteps):
+    """pm2_step_kernel (temporal blocking) against one launch per step: identical uint8 planes for every shape class
+    (one-row / one-column images, strips that touch both borders, ragged last strips, several segments) and for step
+    counts that leave zero or one unfused fp64 step."""
+    h, w = shape
+    rng = np.random.default_rng(1000 * h + w + nsteps)
+    img = [rng.integers(0, 256, size=(h, w), dtype=np.uint8) for _ in range(3)]
+    L = 0.25
+    T = L * (nsteps - 0.5)
+    (a, na), (b, nb) = _pm_both_ways(ctx, img, 12.0, L, T)
+    assert na == nb == nsteps
+    for k in range(3):
+        assert np.array_equal(a[k], b[k]), (shape, nsteps, k, int((a[k] != b[k]).sum()))
+    # and both agree with the oracle within the PM tolerance
+    ref, nr = co.perona_malik(img, 12.0, L, T)
+    assert nr == nsteps
+    _planes_close(b, ref, frac=0.999 if h * w < 2000 else 0.9999)
+
+
+def test_pm_two_steps_per_launch_batch_and_large(ctx):
+    rng = np.random.default_rng(77)
+    imgs = rng.integers(0, 256, size=(5, 3, 96, 130), dtype=np.uint8)
+    (a, na), (b, nb) = _pm_both_ways(ctx, imgs, 20.0, 0.2, 1.3, batch=(5, 3, 96, 130))
+    assert na == nb == 7
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    img = synth.hashed_scene_rows(4096, 4096, 0, 4096, threads=4)
+    (a, na), (b, nb) = _pm_both_ways(ctx, img, 10.0, 0.25, 5.0)
+    assert na == nb == 20
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
