@@ -502,6 +502,7 @@ def run_slabs(args):
     if world == 1 and not args.no_extra:
         extra = {}
         sess.release_scratch()
+        ctx.set_tile_rows(0)  # every configuration with the library's own tile choice
         for name, fp32 in (("C1", False), ("C2", False), ("C3", False), ("C3", True)):
             try:
                 extra[name + ("_fp32" if fp32 else "")] = time_config(h, name, fp32=fp32, reps=2 if name == "C3" else 5)

@@ -74,6 +74,7 @@ SIGNATURES = {
     "cvb_session_region_means": (C.c_int, [vp, C.c_double, f64p, f64p]),
     "cvb_session_download_levelset": (C.c_int, [vp, f64p]),
     "cvb_session_download_image": (C.c_int, [vp, u8pp]),
+    "cvb_session_download_pm_state": (C.c_int, [vp, C.POINTER(f64p)]),
     "cvb_session_mask": (C.c_int, [vp, C.c_int, u8p]),
     "cvb_session_mask_packed": (C.c_int, [vp, C.c_int, u8p]),
     "cvb_session_upload_image_smooth": (C.c_int, [vp, u8pp, C.c_double, C.c_double, C.c_double, intp]),

@@ -116,6 +116,7 @@ struct Job {
     CommView cv{};
     std::vector<void *> ipc_opened;
     unsigned int pm_seq = 0;
+    int pm_cur = -1;  // PM state buffer that holds the input of the last (quantising) step of the newest run; -1: none
 };
 static inline size_t esz(const Job *j) { return j->prec == CVB_PRECISION_F32 ? sizeof(float) : sizeof(double); }
 static inline bool is_f32(const Job *j) { return j->prec == CVB_PRECISION_F32; }
@@ -930,6 +931,7 @@ static cvb_status pm_run_planes(Job *j, int plane0, int np, double K, double L, 
         if (!last) cur = nxt;
         s += fused ? 2 : 1;
     }
+    j->pm_cur = cur;
     if (nsteps == 1) {  // u8 -> fp64 -> u8: the single step cannot write the plane it reads
         if (is_f32(j))
             CU(c, launch_quantise_f32(reinterpret_cast<const float *>(pm[0]), img, (size_t)np * g.plane_elems, c->stream));
@@ -986,16 +988,12 @@ static cvb_status job_upload_image_smooth(Job *j, const uint8_t *const *planes, 
     const int nplanes = g.count * g.nch;
     int nsteps = 0;
     TRY(pm_prepare(j, K, L, T, steps, &nsteps));
-    // CVB_OVERLAP_UPLOAD=0/1 forces the plain / the overlapped sequence.  Default: overlapped on whole images, batches
-    // and P2P row slabs of up to 2 ranks (measured at full size); on more ranks it is verified bit-identical (8 GPUs,
-    // 4096 x 3896) but has not completed a run at the full bench geometry yet, so the plain sequence is the default there
-    static const int overlap_env = [] {
-        const char *e = getenv("CVB_OVERLAP_UPLOAD");
-        return e ? (e[0] == '0' ? 0 : 1) : -1;
-    }();
+    // The overlapped sequence is the default wherever there is something to overlap with (whole images, batches, P2P row
+    // slabs of any rank count); CVB_OVERLAP_UPLOAD=0 forces the plain sequence (upload everything, then diffuse).
+    const char *overlap_env = getenv("CVB_OVERLAP_UPLOAD");
     const bool multi = j->slab && j->ctx->nranks > 1;
     const bool can = !multi || j->p2p;  // NCCL halo exchanges between the launches: nothing to overlap with
-    const bool overlap = can && (overlap_env >= 0 ? overlap_env == 1 : (!multi || j->ctx->nranks <= 2));
+    const bool overlap = can && !(overlap_env && overlap_env[0] == '0');
     if (!overlap || nsteps == 0 || nplanes < 2) {  // nothing to overlap: the plain sequence
         TRY(job_upload_image(j, planes));
         return nsteps ? job_perona_malik(j, K, L, T, nullptr) : CVB_OK;
@@ -1341,6 +1339,24 @@ extern "C" cvb_status cvb_session_download_levelset(cvb_session *s, double *u) {
 }
 extern "C" cvb_status cvb_session_download_image(cvb_session *s, uint8_t *const *planes) {
     return s ? job_download_image(s, 0, s->g.nch, planes) : CVB_ERR_INVALID_ARGUMENT;
+}
+// test hook: the fp64 diffusion state the last (quantising) step of the newest perona_malik run read
+extern "C" cvb_status cvb_session_download_pm_state(cvb_session *s, double *const *planes) {
+    if (!s) return CVB_ERR_INVALID_ARGUMENT;
+    Job *j = s;
+    cvb_context *c = j->ctx;
+    if (!planes || is_f32(j) || j->pm_cur < 0 || !j->d_pm[j->pm_cur])
+        return fail(c, CVB_ERR_STATE, "no fp64 Perona-Malik state (run perona_malik with at least two steps first)");
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    const int rows = g.row_hi - g.row_lo;
+    for (int p = 0; p < g.nch; ++p) {
+        if (!planes[p]) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes[%d] is NULL", p);
+        CU(c, cudaMemcpy2DAsync(planes[p], g.w * sizeof(double), j->d_pm[j->pm_cur] + (size_t)p * g.plane_elems + (size_t)HALO * g.pitch,
+                                g.pitch * sizeof(double), g.w * sizeof(double), rows, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    return CVB_OK;
 }
 extern "C" cvb_status cvb_session_mask(cvb_session *s, int invert, uint8_t *mask) {
     return s ? job_mask(s, 0, invert, mask) : CVB_ERR_INVALID_ARGUMENT;

@@ -390,7 +390,7 @@ constexpr int PM2_STRIP_OWN = 56;
 constexpr int PM2_JNS = 6;  // J ring slots: the prologue of stage B needs 4 rows; 6 keeps every slot offset constant
 constexpr int PM2_SMEM = (PM_RING_NS + PM2_JNS) * PM_RING_SLOT;
 #ifndef PM2_MIN_CTAS
-#define PM2_MIN_CTAS 12
+#define PM2_MIN_CTAS 16
 #endif
 
 template <bool EDGE, bool BROWS>
@@ -834,7 +834,8 @@ __global__ void __launch_bounds__(CTA_THREADS, PM2_MIN_CTAS) pm2_step_kernel(con
     const int w = G.w, h = G.h;
     const double inv_k2 = A.inv_k2, lq = A.L * 0.25;
     const bool interior = cb >= 1 && (cb + 1) * PM2_STRIP_OWN + 4 <= w;
-    const bool brows = ra <= 2 || rb + 2 >= h;  // a stage meets row 0 or row h-1 inside this segment
+    // a stage forces g(0) or g(h-1) inside its row loop: stage A computes g of rows ra-1 .. rb+2, stage B of ra+1 .. rb
+    const bool brows = ra <= 2 || rb + 3 >= h;
     __shared__ __align__(16) unsigned char s_ring[PM2_SMEM];
     unsigned char *jring = s_ring + PM_RING_NS * PM_RING_SLOT;
     if (brows) {

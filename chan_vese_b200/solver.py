@@ -297,6 +297,13 @@ class Session:
         self.ctx.check(self._lib.cvb_session_download_image(self._h, optrs))
         return outs
 
+    def download_pm_state(self):
+        """Test hook: the fp64 planes the last (quantising) Perona-Malik step read."""
+        outs = [np.empty((self.rows, self.w), dtype=np.float64) for _ in range(self.n)]
+        ptrs = (_ffi.f64p * self.n)(*[_f64(a) for a in outs])
+        self.ctx.check(self._lib.cvb_session_download_pm_state(self._h, ptrs))
+        return outs
+
     def mask(self, invert=False, out=None):
         m = out if out is not None else np.empty((self.rows, self.w), dtype=np.uint8)
         self.ctx.check(self._lib.cvb_session_mask(self._h, int(bool(invert)), m.ctypes.data_as(_ffi.u8p)))

@@ -174,13 +174,17 @@ cvb_status cvb_session_csv_step(cvb_session *s, const cvb_csv_params *params, co
 cvb_status cvb_session_region_means(cvb_session *s, double eps, double *c1, double *c2);
 cvb_status cvb_session_download_levelset(cvb_session *s, double *u);
 cvb_status cvb_session_download_image(cvb_session *s, uint8_t *const *planes);
+/* Test hook: the fp64 diffusion state that the last (quantising) step of the newest perona_malik run read, i.e. the
+ * planes after steps - 1 diffusion steps (src/main.cpp:498-550 before :551).  n planes of rows * w doubles. */
+cvb_status cvb_session_download_pm_state(cvb_session *s, double *const *planes);
 cvb_status cvb_session_mask(cvb_session *s, int invert, uint8_t *mask);
 /* The same mask bit-packed: 8 pixels per byte, MSB first, every row padded to (w+7)/8 bytes (numpy.packbits
  * layout along the row) -- 1/8 of the device-to-host traffic.  bits: rows * ((w+7)/8) bytes. */
 cvb_status cvb_session_mask_packed(cvb_session *s, int invert, uint8_t *bits);
 /* upload_image followed by perona_malik, with the host-to-device copies of later planes hidden behind the diffusion
  * of the planes that have already arrived (channels diffuse independently, src/main.cpp:489).  Pinned host memory
- * (cvb_host_alloc) makes the copies truly asynchronous.  Falls back to the plain sequence for row slabs. */
+ * (cvb_host_alloc) makes the copies truly asynchronous.  Row slabs: overlapped when the peers are mapped (the default), the plain
+ * sequence with CVB_COMM=nccl. */
 cvb_status cvb_session_upload_image_smooth(cvb_session *s, const uint8_t *const *planes, double K, double L, double T,
                                            int *steps);
 /* Perona-Malik smooths the resident planes in place (as the reference re-splits img at src/main.cpp:945).
