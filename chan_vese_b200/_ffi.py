@@ -29,6 +29,8 @@ class Stats(C.Structure):
 
 
 FRAME_FN = C.CFUNCTYPE(C.c_int, f64p, C.c_int, C.c_int, C.c_int, vp)
+MASK_FN = C.CFUNCTYPE(C.c_int, u8p, C.c_int, C.c_int, C.c_int, vp)
+MASK_SEPARATE, MASK_CONTOUR = 0, 1
 CsvParamsP = C.POINTER(CsvParams)
 
 # name -> (restype, argtypes); every symbol include/chan_vese_b200.h declares
@@ -55,6 +57,8 @@ SIGNATURES = {
     "cvb_perona_malik": (C.c_int, [vp, u8pp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, u8pp, intp]),
     "cvb_csv_run": (C.c_int, [vp, u8pp, C.c_int, C.c_int, C.c_int, f64p, CsvParamsP, C.c_double, C.c_int, intp, f64p,
                               FRAME_FN, vp]),
+    "cvb_csv_run_masks": (C.c_int, [vp, u8pp, C.c_int, C.c_int, C.c_int, f64p, CsvParamsP, C.c_double, C.c_int, intp, f64p,
+                                    C.c_int, MASK_FN, vp]),
     "cvb_segment": (C.c_int, [vp, u8pp, C.c_int, C.c_int, C.c_int, f64p, C.c_int, C.c_double, C.c_double, C.c_double,
                               u8pp, CsvParamsP, C.c_double, C.c_int, intp, f64p, C.c_int, u8p]),
     "cvb_region_means": (C.c_int, [vp, u8pp, C.c_int, C.c_int, C.c_int, f64p, C.c_double, f64p, f64p]),
@@ -70,6 +74,7 @@ SIGNATURES = {
     "cvb_session_init_checkerboard": (C.c_int, [vp]),
     "cvb_session_perona_malik": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, intp]),
     "cvb_session_csv_run": (C.c_int, [vp, CsvParamsP, C.c_double, C.c_int, intp, f64p, FRAME_FN, vp]),
+    "cvb_session_csv_run_masks": (C.c_int, [vp, CsvParamsP, C.c_double, C.c_int, intp, f64p, C.c_int, MASK_FN, vp]),
     "cvb_session_csv_step": (C.c_int, [vp, CsvParamsP, f64p, f64p, f64p]),
     "cvb_session_region_means": (C.c_int, [vp, C.c_double, f64p, f64p]),
     "cvb_session_download_levelset": (C.c_int, [vp, f64p]),

@@ -12,9 +12,18 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "../../include/chan_vese_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+
+// NVTX range around a solver phase (tracing): cvb.pm / cvb.csv / cvb.upload+pm show up on the
+// timeline of nsys / ncu --nvtx next to the kernels they launch.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 using namespace cvb;
 
@@ -964,6 +973,7 @@ static cvb_status pm_prepare(Job *j, double K, double L, double T, int *steps, i
 
 // perona_malik, src/main.cpp:478-560, on the resident image planes (in place)
 static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *steps) {
+    NvtxRange nvtx("cvb.pm");
     cvb_context *c = j->ctx;
     int nsteps = 0;
     TRY(pm_prepare(j, K, L, T, steps, &nsteps));
@@ -982,6 +992,7 @@ static cvb_status job_perona_malik(Job *j, double K, double L, double T, int *st
 // already arrived (channels diffuse independently, src/main.cpp:489): planes go up in chunks on a copy stream, each
 // chunk's PM launches wait only for that chunk's copy.
 static cvb_status job_upload_image_smooth(Job *j, const uint8_t *const *planes, double K, double L, double T, int *steps) {
+    NvtxRange nvtx("cvb.upload+pm");
     cvb_context *c = j->ctx;
     if (!planes) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes is NULL");
     const Geom &g = j->g;
@@ -1074,6 +1085,7 @@ static cvb_status job_csv_launch_step(Job *j, CsvArgs &A, int step_index /* 0-ba
 // The time-step loop, src/main.cpp:949-1001
 static cvb_status job_csv_run(Job *j, const cvb_csv_params *p, double tol, int max_steps, int *steps_done,
                               double *last_norm, cvb_frame_fn frame, void *user) {
+    NvtxRange nvtx("cvb.csv");
     cvb_context *c = j->ctx;
     TRY(check_params(c, p));
     CU(c, cudaSetDevice(c->device));
@@ -1137,6 +1149,106 @@ static cvb_status job_csv_run(Job *j, const cvb_csv_params *p, double tol, int m
         if (last_norm) last_norm[m] = j->h_state[m].norm;
     }
     return check_peer_timeout(j);
+}
+
+// The time-step loop with an observer of the SEGMENTATION (the seam of vwm.write_frame, src/main.cpp:997, for consumers
+// that draw the contour): after every step the bit-packed mask of the new level set is produced on the device (1/64 of
+// the bytes of u), copied on the copy stream into a ring of pinned host slots together with a snapshot of the solver
+// state, and handed to the callback in step order while later steps are already running.  The loop never waits for the
+// host unless all kRing slots are in flight.
+static cvb_status job_csv_run_masks(Job *j, const cvb_csv_params *p, double tol, int max_steps, int *steps_done, double *last_norm,
+                                    int rule, cvb_mask_fn fn, void *user) {
+    NvtxRange nvtx("cvb.csv+masks");
+    cvb_context *c = j->ctx;
+    TRY(check_params(c, p));
+    const Geom &g = j->g;
+    if (!fn || (rule != 0 && rule != 1)) return fail(c, CVB_ERR_INVALID_ARGUMENT, "mask observer: fn is NULL or unknown rule");
+    if (g.count != 1 || j->slab) return fail(c, CVB_ERR_INVALID_ARGUMENT, "mask observer needs a whole single image");
+    CU(c, cudaSetDevice(c->device));
+    constexpr int kRing = 4;
+    const int rows = g.h, wb = (g.w + 7) / 8;
+    const size_t slot = ((size_t)rows * wb + 255) / 256 * 256, hslot = slot + 256;  // bits, then the state snapshot
+    CsvArgs A;
+    fill_args(j, p, tol, A);
+    TRY(job_fetch_state(j));
+    if (j->h_state[0].steps_done & 1)
+        CU(c, cudaMemcpyAsync(u_plane(j, 0, 0), u_plane(j, 1, 0), (size_t)g.plane_elems * esz(j), cudaMemcpyDeviceToDevice, c->stream));
+    TRY(job_csv_init(j, A, 1));
+    if (!c->copy_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : c->copy_ev) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    struct Ring {  // freed on every exit path
+        uint8_t *d = nullptr, *h = nullptr;
+        cudaEvent_t done[kRing] = {}, copied[kRing] = {};
+        cudaStream_t s0, s1;
+        ~Ring() {
+            cudaStreamSynchronize(s0);
+            cudaStreamSynchronize(s1);
+            cudaFree(d);
+            if (h) cudaFreeHost(h);
+            for (auto e : done)
+                if (e) cudaEventDestroy(e);
+            for (auto e : copied)
+                if (e) cudaEventDestroy(e);
+        }
+    } R;
+    R.s0 = c->stream;
+    R.s1 = c->copy_stream;
+    CU(c, cudaMalloc(&R.d, kRing * hslot));
+    CU(c, cudaMallocHost(&R.h, kRing * hslot));
+    for (int k = 0; k < kRing; ++k) {
+        CU(c, cudaEventCreateWithFlags(&R.done[k], cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&R.copied[k], cudaEventDisableTiming));
+    }
+    const long long limit = max_steps < 0 ? (long long)INT_MAX : (long long)max_steps;  // :890
+    long long launched = 0, delivered = 0;
+    bool stop_launching = false, finished = limit == 0;
+    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    auto deliver = [&]() -> cvb_status {  // the oldest slot in flight (its copy has completed)
+        const int k = (int)(delivered % kRing);
+        CsvState st;
+        memcpy(&st, R.h + k * hslot + slot, sizeof st);
+        ++delivered;
+        if (st.steps_done != delivered) {  // the run had stopped before this launch: it was a no-op, nothing to show
+            stop_launching = finished = true;
+            return CVB_OK;
+        }
+        if (st.done) stop_launching = true;  // the breaking step: shown (its update is applied, :994,:1000), then no more
+        if (fn(R.h + k * hslot, g.h, g.w, (int)delivered, user) != 0)
+            return fail(c, CVB_ERR_CALLBACK, "mask observer aborted the run at step %d", (int)delivered);
+        return CVB_OK;
+    };
+    while (!finished) {
+        if (!stop_launching && launched < limit && launched - delivered < kRing) {
+            const int k = (int)(launched % kRing);
+            TRY(job_csv_launch_step(j, A, (int)(launched & 1)));
+            CU(c, launch_mask_packed(u_plane(j, (int)((launched + 1) & 1), 0) + (size_t)HALO * g.pitch * esz(j), is_f32(j) ? 1 : 0,
+                                     R.d + k * hslot, rows, g.w, g.pitch, 0, c->stream, rule));
+            c->stats.kernel_launches += 1;
+            CU(c, cudaMemcpyAsync(R.d + k * hslot + slot, j->d_state, sizeof(CsvState), cudaMemcpyDeviceToDevice, c->stream));
+            CU(c, cudaEventRecord(R.done[k], c->stream));
+            CU(c, cudaStreamWaitEvent(c->copy_stream, R.done[k], 0));
+            CU(c, cudaMemcpyAsync(R.h + k * hslot, R.d + k * hslot, slot + sizeof(CsvState), cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(c, cudaEventRecord(R.copied[k], c->copy_stream));
+            c->stats.d2h_bytes += (uint64_t)rows * wb + sizeof(CsvState);
+            ++launched;
+            while (delivered < launched && !finished && cudaEventQuery(R.copied[delivered % kRing]) == cudaSuccess) TRY(deliver());
+        } else if (delivered < launched) {
+            CU(c, cudaEventSynchronize(R.copied[delivered % kRing]));
+            TRY(deliver());
+        } else {
+            finished = true;  // everything launched has been shown and nothing more may be launched
+        }
+    }
+    CU(c, cudaEventRecord(c->ev[1], c->stream));
+    TRY(job_fetch_state(j));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->stats.csv_ms += ms;
+    if (steps_done) *steps_done = j->h_state[0].steps_done;
+    if (last_norm) *last_norm = j->h_state[0].norm;
+    return CVB_OK;
 }
 
 static cvb_status job_region_means(Job *j, double eps, double *c1, double *c2, int index) {
@@ -1327,6 +1439,10 @@ extern "C" cvb_status cvb_session_csv_run(cvb_session *s, const cvb_csv_params *
                                           int *steps_done, double *last_norm, cvb_frame_fn frame, void *user) {
     return s ? job_csv_run(s, p, tol, max_steps, steps_done, last_norm, frame, user) : CVB_ERR_INVALID_ARGUMENT;
 }
+extern "C" cvb_status cvb_session_csv_run_masks(cvb_session *s, const cvb_csv_params *p, double tol, int max_steps,
+                                                int *steps_done, double *last_norm, int rule, cvb_mask_fn fn, void *user) {
+    return s ? job_csv_run_masks(s, p, tol, max_steps, steps_done, last_norm, rule, fn, user) : CVB_ERR_INVALID_ARGUMENT;
+}
 extern "C" cvb_status cvb_session_csv_step(cvb_session *s, const cvb_csv_params *p, const double *c1, const double *c2,
                                            double *norm) {
     return s ? job_csv_step(s, p, c1, c2, norm) : CVB_ERR_INVALID_ARGUMENT;
@@ -1484,6 +1600,19 @@ extern "C" cvb_status cvb_csv_run(cvb_context *c, const uint8_t *const *planes, 
     TRY(cvb_session_upload_image(g.s, planes));
     TRY(cvb_session_upload_levelset(g.s, u_inout));
     TRY(cvb_session_csv_run(g.s, params, tol, max_steps, steps_done, last_norm, frame, user));
+    TRY(cvb_session_download_levelset(g.s, u_inout));
+    g.ok = true;
+    return CVB_OK;
+}
+
+extern "C" cvb_status cvb_csv_run_masks(cvb_context *c, const uint8_t *const *planes, int n, int h, int w, double *u_inout,
+                                        const cvb_csv_params *params, double tol, int max_steps, int *steps_done,
+                                        double *last_norm, int rule, cvb_mask_fn fn, void *user) {
+    if (!c) return CVB_ERR_INVALID_ARGUMENT;
+    ONESHOT(g, c, n, h, w);
+    TRY(cvb_session_upload_image(g.s, planes));
+    TRY(cvb_session_upload_levelset(g.s, u_inout));
+    TRY(cvb_session_csv_run_masks(g.s, params, tol, max_steps, steps_done, last_norm, rule, fn, user));
     TRY(cvb_session_download_levelset(g.s, u_inout));
     g.ok = true;
     return CVB_OK;

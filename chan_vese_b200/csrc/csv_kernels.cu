@@ -706,7 +706,9 @@ __global__ void mask_kernel(const double *u, uint8_t *mask, int rows, int w, int
 }
 
 // the same mask, 8 pixels per byte (MSB first), rows padded to whole bytes; u is fp64 or fp32
-__global__ void mask_packed_kernel(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert) {
+// rule 0: separate()'s float32(u) > 0 (src/main.cpp:395-400); rule 1: the video contour's saturate_cast<uchar>(u) > 0, i.e.
+// cvRound(u) >= 1 (src/VideoWriterManager.cpp:65-68)
+__global__ void mask_packed_kernel(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, int rule) {
     const int jb = blockIdx.x * blockDim.x + threadIdx.x;  // byte within the row
     const int wb = (w + 7) / 8;
     if (jb >= wb) return;
@@ -716,9 +718,15 @@ __global__ void mask_packed_kernel(const void *u, int f32, uint8_t *bits, int ro
             const int j = jb * 8 + k;
             unsigned int m = 0;
             if (j < w) {
-                const float v = f32 ? reinterpret_cast<const float *>(u)[(size_t)i * pitch + j]
-                                    : __double2float_rn(reinterpret_cast<const double *>(u)[(size_t)i * pitch + j]);
-                m = (v > 0.0f) ? 1u : 0u;
+                if (rule == 1) {
+                    const double x = f32 ? (double)reinterpret_cast<const float *>(u)[(size_t)i * pitch + j]
+                                         : reinterpret_cast<const double *>(u)[(size_t)i * pitch + j];
+                    m = (__double2int_rn(x) >= 1) ? 1u : 0u;  // round half to even, saturation keeps the sign
+                } else {
+                    const float v = f32 ? reinterpret_cast<const float *>(u)[(size_t)i * pitch + j]
+                                        : __double2float_rn(reinterpret_cast<const double *>(u)[(size_t)i * pitch + j]);
+                    m = (v > 0.0f) ? 1u : 0u;
+                }
                 if (invert) m ^= 1u;
             }
             b |= m << (7 - k);
@@ -856,9 +864,10 @@ cudaError_t launch_mask(const double *u, uint8_t *mask, int rows, int w, int pit
     mask_kernel<<<grid, 256, 0, s>>>(u, mask, rows, w, pitch, invert);
     return cudaGetLastError();
 }
-cudaError_t launch_mask_packed(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, cudaStream_t s) {
+cudaError_t launch_mask_packed(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, cudaStream_t s,
+                               int rule) {
     dim3 grid(((w + 7) / 8 + 127) / 128, std::min(rows, 65535));
-    mask_packed_kernel<<<grid, 128, 0, s>>>(u, f32, bits, rows, w, pitch, invert);
+    mask_packed_kernel<<<grid, 128, 0, s>>>(u, f32, bits, rows, w, pitch, invert, rule);
     return cudaGetLastError();
 }
 cudaError_t launch_mask_packed_batch(const void *u0, const void *u1, const CsvState *state, int f32, uint8_t *bits, int count,

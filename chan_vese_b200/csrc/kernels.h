@@ -42,7 +42,9 @@ cudaError_t launch_csv_init(const CsvArgs &A, int final_mode, cudaStream_t s);
 cudaError_t launch_csv_finalize(const CsvArgs &A, int mode, cudaStream_t s);
 cudaError_t launch_delta_map(double *data, size_t n, double eps, cudaStream_t s);
 cudaError_t launch_mask(const double *u, uint8_t *mask, int rows, int w, int pitch, int invert, cudaStream_t s);
-cudaError_t launch_mask_packed(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, cudaStream_t s);
+// rule 0: separate()'s float32(u) > 0; rule 1: the video contour's saturate_cast<uchar>(u) > 0 (u > 0.5)
+cudaError_t launch_mask_packed(const void *u, int f32, uint8_t *bits, int rows, int w, int pitch, int invert, cudaStream_t s,
+                               int rule = 0);
 // all images of a batch: bits = [count][rows][(w+7)/8]; each image's current buffer is picked from its own step counter
 cudaError_t launch_mask_packed_batch(const void *u0, const void *u1, const CsvState *state, int f32, uint8_t *bits, int count,
                                      int rows, int w, int pitch, size_t plane_bytes, int invert, cudaStream_t s);

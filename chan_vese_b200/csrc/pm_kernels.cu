@@ -73,7 +73,7 @@ __device__ __forceinline__ double edge_stop(double gx, double gy, double K, doub
         const double mag = __dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy));
         return __ddiv_rn(1.0, __dadd_rn(1.0, __ddiv_rn(mag, __dmul_rn(K, K))));
     } else {
-        const double mag = fma(gx, gx, gy * gy);
+        const double mag = fma(gx, gx, __dmul_rn(gy, gy));
         return fast_rcp(fma(mag, inv_k2, 1.0));
     }
 }
@@ -133,7 +133,7 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
         rd.y = E2 - X.x;
         rs.y = fma(2.0, X.y, X.x) + E2;
     };
-    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, gy * gy), inv_k2, 1.0)); };  // :518-521
+    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, __dmul_rn(gy, gy)), inv_k2, 1.0)); };  // :518-521
 
     // prologue: rows ra-2 .. ra+1 give g(ra-1), g(ra) and the flux Fy(ra-1/2)
     const double2 X0 = ldr(pin), X1 = ldr(pin + pitch), X2 = ldr(pin + 2 * pitch),
@@ -144,14 +144,14 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
     sobel_rows(X2, rd2, rs2);
     sobel_rows(X3, rd3, rs3);
     double2 gP, gC;  // g(ra-1), g(ra)
-    gP.x = edge((rd0.x + 2.0 * rd1.x) + rd2.x, rs2.x - rs0.x);
-    gP.y = edge((rd0.y + 2.0 * rd1.y) + rd2.y, rs2.y - rs0.y);
-    gC.x = edge((rd1.x + 2.0 * rd2.x) + rd3.x, rs3.x - rs1.x);
-    gC.y = edge((rd1.y + 2.0 * rd2.y) + rd3.y, rs3.y - rs1.y);
+    gP.x = edge(fma(2.0, rd1.x, rd0.x) + rd2.x, rs2.x - rs0.x);
+    gP.y = edge(fma(2.0, rd1.y, rd0.y) + rd2.y, rs2.y - rs0.y);
+    gC.x = edge(fma(2.0, rd2.x, rd1.x) + rd3.x, rs3.x - rs1.x);
+    gC.y = edge(fma(2.0, rd2.y, rd1.y) + rd3.y, rs3.y - rs1.y);
     if (ra == 0 || ra == G.h - 1) gC = make_double2(1.0, 1.0);  // g = 1 on the image border rows (:516)
     fixg(gP);
     fixg(gC);
-    double fy0 = (gP.x + gC.x) * (X2.x - X1.x), fy1 = (gP.y + gC.y) * (X2.y - X1.y);  // Fy(ra-1/2); 0 at the image top
+    double fy0 = __dmul_rn(gP.x + gC.x, X2.x - X1.x), fy1 = __dmul_rn(gP.y + gC.y, X2.y - X1.y);  // Fy(ra-1/2); 0 at the image top
     double2 IC = X2, IS = X3;                                                  // rows i, i+1
     double2 P = make_double2(fma(2.0, rd3.x, rd2.x), fma(2.0, rd3.y, rd2.y));  // rd(i) + 2 rd(i+1)
     double2 rdB = rd3;                                                         // rd(i+1)
@@ -177,19 +177,21 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
         fixg(gS);
         // fluxes of row i and the update (:524-548); at the image top/bottom the halo rows hold copies of the border
         // rows (clamped neighbours, :527-528), so the fluxes across the border are exactly zero
-        const double fs0 = (gC.x + gS.x) * (IS.x - IC.x), fs1 = (gC.y + gS.y) * (IS.y - IC.y);  // Fy(i+1/2)
+        const double fs0 = __dmul_rn(gC.x + gS.x, IS.x - IC.x), fs1 = __dmul_rn(gC.y + gS.y, IS.y - IC.y);  // Fy(i+1/2)
         const double Ie = __shfl_down_sync(0xffffffffu, IC.x, 1);
         const double ge = __shfl_down_sync(0xffffffffu, gC.x, 1);
-        double fx0 = (gC.x + gC.y) * (IC.y - IC.x);        // Fx(a+1/2)
-        double fx1 = (gC.y + ge) * (Ie - IC.y);            // Fx(a+3/2)
+        // Fx(a+1/2) = g0 * d0 enters both pixels and nothing else: it is folded into two explicit FMAs
+        const double g0 = gC.x + gC.y;
+        double d0 = IC.y - IC.x;
+        double fx1 = __dmul_rn(gC.y + ge, Ie - IC.y);      // Fx(a+3/2)
         if (EDGE) {
-            fx0 = nofx0 ? 0.0 : fx0;
+            d0 = nofx0 ? 0.0 : d0;
             fx1 = bc1 ? 0.0 : fx1;
         }
         double fxw = __shfl_up_sync(0xffffffffu, fx1, 1);  // Fx(a-1/2)
         if (EDGE) fxw = nofxw ? 0.0 : fxw;
-        const double o0 = fma((fs0 - fy0) + (fx0 - fxw), lq, IC.x);
-        const double o1 = fma((fs1 - fy1) + (fx1 - fx0), lq, IC.y);
+        const double o0 = fma((fs0 - fy0) + fma(g0, d0, -fxw), lq, IC.x);
+        const double o1 = fma((fs1 - fy1) + fma(-g0, d0, fx1), lq, IC.y);
         if (EDGE) {
             if (lane >= 1 && lane <= 30 && a < w) pm_store(po, o0, o1, a + 1 < w);
         } else if (lane >= 1 && lane <= 30) {
@@ -265,7 +267,7 @@ __device__ __forceinline__ void pm_rows_ring(const double *__restrict__ in, TOUT
         rd.y = r.E2 - r.X.x;
         rs.y = fma(2.0, r.X.y, r.X.x) + r.E2;
     };
-    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, gy * gy), inv_k2, 1.0)); };  // :518-521
+    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, __dmul_rn(gy, gy)), inv_k2, 1.0)); };  // :518-521
 
     // ring rows 0 .. NS-1, two per group
 #pragma unroll
@@ -284,14 +286,14 @@ __device__ __forceinline__ void pm_rows_ring(const double *__restrict__ in, TOUT
     sobel_rows(Q2, rd2, rs2);
     sobel_rows(Q3, rd3, rs3);
     double2 gP, gC;  // g(ra-1), g(ra)
-    gP.x = edge((rd0.x + 2.0 * rd1.x) + rd2.x, rs2.x - rs0.x);
-    gP.y = edge((rd0.y + 2.0 * rd1.y) + rd2.y, rs2.y - rs0.y);
-    gC.x = edge((rd1.x + 2.0 * rd2.x) + rd3.x, rs3.x - rs1.x);
-    gC.y = edge((rd1.y + 2.0 * rd2.y) + rd3.y, rs3.y - rs1.y);
+    gP.x = edge(fma(2.0, rd1.x, rd0.x) + rd2.x, rs2.x - rs0.x);
+    gP.y = edge(fma(2.0, rd1.y, rd0.y) + rd2.y, rs2.y - rs0.y);
+    gC.x = edge(fma(2.0, rd2.x, rd1.x) + rd3.x, rs3.x - rs1.x);
+    gC.y = edge(fma(2.0, rd2.y, rd1.y) + rd3.y, rs3.y - rs1.y);
     if (ra == 0 || ra == G.h - 1) gC = make_double2(1.0, 1.0);  // g = 1 on the image border rows (:516)
     fixg(gP);
     fixg(gC);
-    double fy0 = (gP.x + gC.x) * (Q2.X.x - Q1.X.x), fy1 = (gP.y + gC.y) * (Q2.X.y - Q1.X.y);  // Fy(ra-1/2)
+    double fy0 = __dmul_rn(gP.x + gC.x, Q2.X.x - Q1.X.x), fy1 = __dmul_rn(gP.y + gC.y, Q2.X.y - Q1.X.y);  // Fy(ra-1/2)
     double2 IC = Q2.X, IS = Q3.X;                                              // rows i, i+1
     double ICe = Q2.E2, ISe = Q3.E2;                                           // their east neighbours (column a+2)
     double2 P = make_double2(fma(2.0, rd3.x, rd2.x), fma(2.0, rd3.y, rd2.y));  // rd(i) + 2 rd(i+1)
@@ -312,18 +314,19 @@ __device__ __forceinline__ void pm_rows_ring(const double *__restrict__ in, TOUT
         fixg(gS);
         // fluxes of row i and the update (:524-548); at the image top/bottom the halo rows hold copies of the border
         // rows (clamped neighbours, :527-528), so the fluxes across the border are exactly zero
-        const double fs0 = (gC.x + gS.x) * (IS.x - IC.x), fs1 = (gC.y + gS.y) * (IS.y - IC.y);  // Fy(i+1/2)
+        const double fs0 = __dmul_rn(gC.x + gS.x, IS.x - IC.x), fs1 = __dmul_rn(gC.y + gS.y, IS.y - IC.y);  // Fy(i+1/2)
         const double ge = __shfl_down_sync(0xffffffffu, gC.x, 1);
-        double fx0 = (gC.x + gC.y) * (IC.y - IC.x);        // Fx(a+1/2)
-        double fx1 = (gC.y + ge) * (ICe - IC.y);           // Fx(a+3/2)
+        const double g0 = gC.x + gC.y;                     // Fx(a+1/2) = g0 * d0, folded into the two FMAs below
+        double d0 = IC.y - IC.x;
+        double fx1 = __dmul_rn(gC.y + ge, ICe - IC.y);     // Fx(a+3/2)
         if (EDGE) {
-            fx0 = nofx0 ? 0.0 : fx0;
+            d0 = nofx0 ? 0.0 : d0;
             fx1 = bc1 ? 0.0 : fx1;
         }
         double fxw = __shfl_up_sync(0xffffffffu, fx1, 1);  // Fx(a-1/2)
         if (EDGE) fxw = nofxw ? 0.0 : fxw;
-        const double o0 = fma((fs0 - fy0) + (fx0 - fxw), lq, IC.x);
-        const double o1 = fma((fs1 - fy1) + (fx1 - fx0), lq, IC.y);
+        const double o0 = fma((fs0 - fy0) + fma(g0, d0, -fxw), lq, IC.x);
+        const double o1 = fma((fs1 - fy1) + fma(-g0, d0, fx1), lq, IC.y);
         if (EDGE) {
             if (lane >= 1 && lane <= 30 && a < w) pm_store(po, o0, o1, a + 1 < w);
         } else if (lane >= 1 && lane <= 30) {
@@ -382,6 +385,8 @@ __device__ __forceinline__ void pm_rows_ring(const double *__restrict__ in, TOUT
 // The stencil of two steps has radius 4: lanes 0, 1, 30 and 31 are halo lanes (a strip owns 56 columns), stage A needs
 // I rows ra-4 .. rb+3 (HALO = 4 rows around every slab).  Bit-identical to two single launches: every J value is the
 // double the first launch would have stored, every operation of stage B the one the second launch would execute.
+// (For that to hold whatever the compiler does, no multiplication that feeds an addition is left to FMA contraction in
+// ANY of the fast row functions of this file: flux products are __dmul_rn, everything else is an explicit fma or an add.)
 // Image borders: g = 1 on the border rows and columns and zero flux across them in BOTH stages (:516, :527-530).  The
 // J rows above row 0 / below row h-1 that stage A makes out of the replicated halo rows are NOT copies of J(0) / J(h-1),
 // as the clamped neighbours of the second step require; stage B therefore takes the flux across the top border as
@@ -437,7 +442,7 @@ __device__ __forceinline__ void pm2_rows_ring(const double *__restrict__ in, dou
         rd.y = r.E2 - r.X.x;
         rs.y = fma(2.0, r.X.y, r.X.x) + r.E2;
     };
-    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, gy * gy), inv_k2, 1.0)); };  // :518-521
+    auto edge = [&](double gx, double gy) { return fast_rcp(fma(fma(gx, gx, __dmul_rn(gy, gy)), inv_k2, 1.0)); };  // :518-521
 
     // what one diffusion step carries from row to row (the locals of pm_rows_ring)
     struct Carry {
@@ -457,15 +462,15 @@ __device__ __forceinline__ void pm2_rows_ring(const double *__restrict__ in, dou
         sobel_rows(Q2, rd2, rs2);
         sobel_rows(Q3, rd3, rs3);
         double2 gP;
-        gP.x = edge((rd0.x + 2.0 * rd1.x) + rd2.x, rs2.x - rs0.x);
-        gP.y = edge((rd0.y + 2.0 * rd1.y) + rd2.y, rs2.y - rs0.y);
-        c.gC.x = edge((rd1.x + 2.0 * rd2.x) + rd3.x, rs3.x - rs1.x);
-        c.gC.y = edge((rd1.y + 2.0 * rd2.y) + rd3.y, rs3.y - rs1.y);
+        gP.x = edge(fma(2.0, rd1.x, rd0.x) + rd2.x, rs2.x - rs0.x);
+        gP.y = edge(fma(2.0, rd1.y, rd0.y) + rd2.y, rs2.y - rs0.y);
+        c.gC.x = edge(fma(2.0, rd2.x, rd1.x) + rd3.x, rs3.x - rs1.x);
+        c.gC.y = edge(fma(2.0, rd2.y, rd1.y) + rd3.y, rs3.y - rs1.y);
         if (i == 0 || i == h - 1) c.gC = make_double2(1.0, 1.0);  // g = 1 on the image border rows (:516)
         fixg(gP);
         fixg(c.gC);
-        c.fy0 = (gP.x + c.gC.x) * (Q2.X.x - Q1.X.x);
-        c.fy1 = (gP.y + c.gC.y) * (Q2.X.y - Q1.X.y);
+        c.fy0 = __dmul_rn(gP.x + c.gC.x, Q2.X.x - Q1.X.x);
+        c.fy1 = __dmul_rn(gP.y + c.gC.y, Q2.X.y - Q1.X.y);
         if (BROWS && zero_top_flux && i == 0) c.fy0 = c.fy1 = 0.0;  // stage B: J(-1) := J(0)
         c.IC = Q2.X;
         c.IS = Q3.X;
@@ -485,18 +490,19 @@ __device__ __forceinline__ void pm2_rows_ring(const double *__restrict__ in, dou
         gS.y = edge(c.P.y + rdC.y, rsC.y - c.rsA.y);
         if (BROWS && (i + 1 == 0 || i + 1 == h - 1)) gS = make_double2(1.0, 1.0);  // g = 1 on the border rows (:516)
         fixg(gS);
-        const double fs0 = (c.gC.x + gS.x) * (c.IS.x - c.IC.x), fs1 = (c.gC.y + gS.y) * (c.IS.y - c.IC.y);  // Fy(i+1/2)
+        const double fs0 = __dmul_rn(c.gC.x + gS.x, c.IS.x - c.IC.x), fs1 = __dmul_rn(c.gC.y + gS.y, c.IS.y - c.IC.y);  // Fy(i+1/2)
         const double ge = __shfl_down_sync(0xffffffffu, c.gC.x, 1);
-        double fx0 = (c.gC.x + c.gC.y) * (c.IC.y - c.IC.x);  // Fx(a+1/2)
-        double fx1 = (c.gC.y + ge) * (c.ICe - c.IC.y);       // Fx(a+3/2)
+        const double g0 = c.gC.x + c.gC.y;                    // Fx(a+1/2) = g0 * d0, folded into the two FMAs below
+        double d0 = c.IC.y - c.IC.x;
+        double fx1 = __dmul_rn(c.gC.y + ge, c.ICe - c.IC.y);  // Fx(a+3/2)
         if (EDGE) {
-            fx0 = nofx0 ? 0.0 : fx0;
+            d0 = nofx0 ? 0.0 : d0;
             fx1 = bc1 ? 0.0 : fx1;
         }
         double fxw = __shfl_up_sync(0xffffffffu, fx1, 1);  // Fx(a-1/2)
         if (EDGE) fxw = nofxw ? 0.0 : fxw;
-        o0 = fma((fs0 - c.fy0) + (fx0 - fxw), lq, c.IC.x);
-        o1 = fma((fs1 - c.fy1) + (fx1 - fx0), lq, c.IC.y);
+        o0 = fma((fs0 - c.fy0) + fma(g0, d0, -fxw), lq, c.IC.x);
+        o1 = fma((fs1 - c.fy1) + fma(-g0, d0, fx1), lq, c.IC.y);
         c.fy0 = fs0;
         c.fy1 = fs1;
         c.P.x = fma(2.0, rdC.x, c.rdB.x);

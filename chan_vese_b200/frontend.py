@@ -9,7 +9,7 @@ build this image has.  What the C++ front-end cannot do and this one can (SURVEY
   * any image format cv2.imread knows (src/main.cpp:877-881);
   * -V: the per-step video "<stem>.avi" of the contour over the ORIGINAL image, frame 0 = the initial level set, one
     frame per CSV step, optional "t = n" overlay text (VideoWriterManager, src/VideoWriterManager.cpp:24-127; frames
-    are fed by the per-step observer of the C ABI, cvb_frame_fn);
+    are fed by the asynchronous per-step mask observer of the C ABI, cvb_mask_fn);
   * --rect x,y,w,h / --circ cx,cy,r replace the interactive window of -R / -C (src/main.cpp:899-921).
 
 All numerics run in the CUDA library through chan_vese_b200.Context; there is no CPU path here either.  `backend`
@@ -63,8 +63,12 @@ class VideoWriterManager:
 
     def draw_contour(self, dst, u):
         """:57-75.  Note the threshold: saturate_cast<uchar>(u) > 0, i.e. u > 0.5 -- not the u > 0 of separate()."""
+        return self.draw_contour_mask(dst, (saturate_u8(u) > 0).astype(np.uint8))
+
+    def draw_contour_mask(self, dst, mask):
+        """The same from the 0/1 mask itself (the per-step mask observer of the C ABI delivers it: CVB_MASK_CONTOUR)."""
         cv2 = self.cv2
-        mask = (saturate_u8(u) > 0).astype(np.uint8)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
         cs, hier = cv2.findContours(mask, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
         if hier is None:  # no contour at all: the reference would index an empty hierarchy
             return 0
@@ -95,9 +99,12 @@ class VideoWriterManager:
         color = COLORS["black"] if 255 - intensity < 105 else COLORS["white"]
         return color, p
 
-    def compose(self, u, overlay_text=""):
+    def compose(self, u, overlay_text="", mask=None):
         frame = self.img.copy()
-        self.draw_contour(frame, u)
+        if mask is not None:
+            self.draw_contour_mask(frame, mask)
+        else:
+            self.draw_contour(frame, u)
         if self.enable_overlay:
             color, p = self.overlay_color(overlay_text)
             self.cv2.putText(frame, overlay_text, p, self.cv2.FONT_HERSHEY_PLAIN, self.FONT_SCALE, color, self.FONT_THICKNESS,
@@ -107,6 +114,11 @@ class VideoWriterManager:
     def write_frame(self, u, overlay_text=""):
         """:41-54."""
         self.vw.write(self.compose(u, overlay_text))
+        self.frames += 1
+
+    def write_mask_frame(self, mask, overlay_text=""):
+        """write_frame for a consumer that received the thresholded level set instead of the level set."""
+        self.vw.write(self.compose(None, overlay_text, mask=mask))
         self.frames += 1
 
     def release(self):
@@ -256,7 +268,15 @@ def run(argv, backend=None, video_writer=None):
                 vwm.write_frame(uu, ("t = %d" % step) if o.overlay_text else "")
                 return 0
         params = cv.make_params(o.mu, o.nu, o.dt, o.epsilon, o.lambda1, o.lambda2, nch=nch)
-        u, steps, norm = backend.csv_run(channels, u, params, o.tolerance, o.max_steps, frame)
+        if vwm is not None and hasattr(backend, "csv_run_masks"):
+            # the CUDA backend streams the per-step contour masks (1/64 of the bytes of u) through a pinned ring while
+            # later steps run; the frames are the same as those drawn from u (same threshold, VideoWriterManager.cpp:65-68)
+            def on_mask(m, step):
+                vwm.write_mask_frame(m, ("t = %d" % step) if o.overlay_text else "")
+                return 0
+            u, steps, norm = backend.csv_run_masks(channels, u, params, on_mask, o.tolerance, o.max_steps, contour_rule=True)
+        else:
+            u, steps, norm = backend.csv_run(channels, u, params, o.tolerance, o.max_steps, frame)
         if vwm is not None:
             vwm.release()
         if o.select:  # :1004-1005, separate() :386-405

@@ -151,6 +151,19 @@ class Context:
                                          C.byref(steps), C.byref(norm), cb, None))
         return u, steps.value, norm.value
 
+    def csv_run_masks(self, channels, u, params, on_mask, tol=1e-3, max_steps=-1, contour_rule=True):
+        """The time-step loop with the asynchronous per-step mask observer: on_mask(mask01 (h, w) uint8, step) -> truthy
+        aborts.  contour_rule: VideoWriterManager's u > 0.5 (True) or separate()'s float32(u) > 0 (False)."""
+        arrs, ptrs = _planes(channels)
+        h, w = arrs[0].shape
+        u = np.array(u, dtype=np.float64, order="C", copy=True)
+        steps, norm = C.c_int(0), C.c_double(0.0)
+        cb = _wrap_mask_fn(on_mask, h, w)
+        self.check(self._lib.cvb_csv_run_masks(self._h, ptrs, len(arrs), h, w, _f64(u), C.byref(params), tol, int(max_steps),
+                                               C.byref(steps), C.byref(norm),
+                                               _ffi.MASK_CONTOUR if contour_rule else _ffi.MASK_SEPARATE, cb, None))
+        return u, steps.value, norm.value
+
     def segment(self, channels, u, params, tol=1e-3, max_steps=-1, smooth=False, K=10.0, L=0.25, T=20.0, invert=False):
         arrs, ptrs = _planes(channels)
         h, w = arrs[0].shape
@@ -198,6 +211,19 @@ class Context:
         m = np.empty((h, w), dtype=np.uint8)
         self.check(self._lib.cvb_mask(self._h, _f64(u), h, w, int(bool(invert)), m.ctypes.data_as(_ffi.u8p)))
         return m
+
+
+def _wrap_mask_fn(fn, h, w):
+    wb = (w + 7) // 8
+
+    def _cb(bits, hh, ww, step, _user):
+        try:
+            packed = np.ctypeslib.as_array(bits, shape=(hh, wb))
+            return int(bool(fn(np.unpackbits(packed, axis=1)[:, :ww], step)))
+        except Exception:  # never let an exception cross the ABI
+            return 1
+
+    return _ffi.MASK_FN(_cb)
 
 
 def _wrap_frame(frame, h, w):
@@ -269,6 +295,14 @@ class Session:
         cb = _wrap_frame(frame, self.h, self.w)
         self.ctx.check(self._lib.cvb_session_csv_run(self._h, C.byref(params), tol, int(max_steps), C.byref(steps),
                                                      C.byref(norm), cb, None))
+        return steps.value, norm.value
+
+    def csv_run_masks(self, params, on_mask, tol=1e-3, max_steps=-1, contour_rule=True):
+        steps, norm = C.c_int(0), C.c_double(0.0)
+        cb = _wrap_mask_fn(on_mask, self.h, self.w)
+        self.ctx.check(self._lib.cvb_session_csv_run_masks(self._h, C.byref(params), tol, int(max_steps), C.byref(steps),
+                                                           C.byref(norm),
+                                                           _ffi.MASK_CONTOUR if contour_rule else _ffi.MASK_SEPARATE, cb, None))
         return steps.value, norm.value
 
     def csv_step(self, params, c1=None, c2=None):

@@ -77,6 +77,13 @@ typedef struct cvb_batch cvb_batch;     /* a batch of independent equal-sized im
  * valid during the call.  Return non-zero to abort the run (CVB_ERR_CALLBACK). */
 typedef int (*cvb_frame_fn)(const double *u, int h, int w, int step, void *user);
 
+/* Per-step observer of the SEGMENTATION: the bit-packed mask (numpy.packbits layout along each row, (w+7)/8 bytes per
+ * row) of the level set after `step` steps -- what a consumer that draws the contour needs (src/VideoWriterManager.cpp:
+ * 57-75), at 1/64 of the bytes of u.  bits is a pinned host buffer, valid during the call.  Non-zero return aborts. */
+typedef int (*cvb_mask_fn)(const uint8_t *bits, int h, int w, int step, void *user);
+#define CVB_MASK_SEPARATE 0 /* float32(u) > 0: separate(), src/main.cpp:395-400 */
+#define CVB_MASK_CONTOUR 1  /* saturate_cast<uchar>(u) > 0, i.e. u > 0.5: VideoWriterManager::draw_contour, :65-68 */
+
 /* ---- library / context ------------------------------------------------------------------------ */
 const char *cvb_version(void);
 int cvb_device_count(void); /* number of CUDA devices, 0 if none / no driver */
@@ -130,6 +137,12 @@ cvb_status cvb_perona_malik(cvb_context *ctx, const uint8_t *const *planes_in, i
 cvb_status cvb_csv_run(cvb_context *ctx, const uint8_t *const *planes, int n, int h, int w, double *u_inout,
                        const cvb_csv_params *params, double tol, int max_steps, int *steps_done,
                        double *last_norm, cvb_frame_fn frame, void *user);
+/* The same loop with the asynchronous mask observer instead of the synchronous level-set observer: masks are produced
+ * on the device after every step, travel on a second stream through a ring of pinned buffers and reach fn in step
+ * order while later steps are already running (the solver never waits for the host unless 4 masks are in flight). */
+cvb_status cvb_csv_run_masks(cvb_context *ctx, const uint8_t *const *planes, int n, int h, int w, double *u_inout,
+                             const cvb_csv_params *params, double tol, int max_steps, int *steps_done,
+                             double *last_norm, int rule, cvb_mask_fn fn, void *user);
 /* PM (optional) followed by CSV with the smoothed planes staying in HBM: main()'s :939-1001.
  * planes_pm_out (optional) receives the uint8 PM result (the "_pm" image, :946); mask_out (optional)
  * receives separate()'s mask (:395-400). */
@@ -166,6 +179,8 @@ cvb_status cvb_session_init_checkerboard(cvb_session *s);
 cvb_status cvb_session_perona_malik(cvb_session *s, double K, double L, double T, int *steps);
 cvb_status cvb_session_csv_run(cvb_session *s, const cvb_csv_params *params, double tol, int max_steps,
                                int *steps_done, double *last_norm, cvb_frame_fn frame, void *user);
+cvb_status cvb_session_csv_run_masks(cvb_session *s, const cvb_csv_params *params, double tol, int max_steps,
+                                     int *steps_done, double *last_norm, int rule, cvb_mask_fn fn, void *user);
 /* One CSV step.  c1/c2 == NULL: region means of the current u are used (as the loop does);
  * otherwise the given means are used (test hook).  *norm (optional) receives ||du||_2. */
 cvb_status cvb_session_csv_step(cvb_session *s, const cvb_csv_params *params, const double *c1,

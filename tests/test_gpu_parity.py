@@ -612,3 +612,35 @@ def test_pm_two_steps_per_launch_batch_and_large(ctx):
     (a, na), (b, nb) = _pm_both_ways(ctx, img, 10.0, 0.25, 5.0)
     assert na == nb == 20
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+# ---- asynchronous per-step mask observer (src/main.cpp:997, VideoWriterManager.cpp:57-75) -----------------
+@pytest.mark.parametrize("contour_rule", [True, False])
+@pytest.mark.parametrize("tol,max_steps", [(0.0, 23), (0.05, 200)])
+def test_async_mask_observer_matches_the_level_set_frames(ctx, contour_rule, tol, max_steps):
+    """The masks that travel through the pinned ring while later steps run are, step for step, the threshold of the
+    level sets the synchronous observer shows -- same steps, same order, the breaking step included, nothing after it."""
+    h, w = 91, 150
+    img = synth.seastar(h, w, seed=31)
+    u0 = cv.levelset_checkerboard(h, w)
+    prm = cv.make_params()
+    frames, masks = [], []
+    u1, s1, n1 = ctx.csv_run(img, u0, prm, tol=tol, max_steps=max_steps, frame=lambda u, step: frames.append((step, u.copy())) and 0)
+    u2, s2, n2 = ctx.csv_run_masks(img, u0, prm, lambda m, step: masks.append((step, m.copy())) and 0, tol=tol,
+                                   max_steps=max_steps, contour_rule=contour_rule)
+    assert s1 == s2 and n1 == n2 and np.array_equal(u1, u2)
+    assert [s for s, _ in frames] == [s for s, _ in masks] == list(range(1, s1 + 1))
+    if tol > 0:
+        assert s1 < max_steps  # the tolerance ended the run
+    for (_, u), (_, m) in zip(frames, masks):
+        ref = (np.clip(np.rint(u), 0, 255) > 0) if contour_rule else (u.astype(np.float32) > 0)
+        assert np.array_equal(m.astype(bool), ref)
+
+
+def test_async_mask_observer_abort(ctx):
+    img = synth.seastar(64, 80, seed=3)
+    u0 = cv.levelset_checkerboard(64, 80)
+    seen = []
+    with pytest.raises(cv.ChanVeseError) as e:
+        ctx.csv_run_masks(img, u0, cv.make_params(), lambda m, step: seen.append(step) or step == 3, tol=0.0, max_steps=50)
+    assert "CALLBACK" in str(e.value) and seen == [1, 2, 3]
