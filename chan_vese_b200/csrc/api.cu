@@ -1167,7 +1167,8 @@ static cvb_status job_csv_run_masks(Job *j, const cvb_csv_params *p, double tol,
     CU(c, cudaSetDevice(c->device));
     constexpr int kRing = 4;
     const int rows = g.h, wb = (g.w + 7) / 8;
-    const size_t slot = ((size_t)rows * wb + 255) / 256 * 256, hslot = slot + 256;  // bits, then the state snapshot
+    const size_t slot = ((size_t)rows * wb + 255) / 256 * 256;              // bits ...
+    const size_t hslot = slot + (sizeof(CsvState) + 255) / 256 * 256;       // ... then the state snapshot
     CsvArgs A;
     fill_args(j, p, tol, A);
     TRY(job_fetch_state(j));

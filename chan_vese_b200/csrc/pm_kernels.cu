@@ -181,10 +181,11 @@ __device__ __forceinline__ void pm_rows_fast(const TIN *__restrict__ in, TOUT *_
         const double Ie = __shfl_down_sync(0xffffffffu, IC.x, 1);
         const double ge = __shfl_down_sync(0xffffffffu, gC.x, 1);
         // Fx(a+1/2) = g0 * d0 enters both pixels and nothing else: it is folded into two explicit FMAs
-        const double g0 = gC.x + gC.y;
+        double g0 = gC.x + gC.y;
         double d0 = IC.y - IC.x;
         double fx1 = __dmul_rn(gC.y + ge, Ie - IC.y);      // Fx(a+3/2)
         if (EDGE) {
+            g0 = nofx0 ? 0.0 : g0;  // no flux across the right border; g of the column beyond it may be anything (NaN included)
             d0 = nofx0 ? 0.0 : d0;
             fx1 = bc1 ? 0.0 : fx1;
         }
@@ -316,10 +317,11 @@ __device__ __forceinline__ void pm_rows_ring(const double *__restrict__ in, TOUT
         // rows (clamped neighbours, :527-528), so the fluxes across the border are exactly zero
         const double fs0 = __dmul_rn(gC.x + gS.x, IS.x - IC.x), fs1 = __dmul_rn(gC.y + gS.y, IS.y - IC.y);  // Fy(i+1/2)
         const double ge = __shfl_down_sync(0xffffffffu, gC.x, 1);
-        const double g0 = gC.x + gC.y;                     // Fx(a+1/2) = g0 * d0, folded into the two FMAs below
+        double g0 = gC.x + gC.y;                           // Fx(a+1/2) = g0 * d0, folded into the two FMAs below
         double d0 = IC.y - IC.x;
         double fx1 = __dmul_rn(gC.y + ge, ICe - IC.y);     // Fx(a+3/2)
         if (EDGE) {
+            g0 = nofx0 ? 0.0 : g0;  // no flux across the right border; g of the column beyond it may be anything (NaN included)
             d0 = nofx0 ? 0.0 : d0;
             fx1 = bc1 ? 0.0 : fx1;
         }
@@ -492,10 +494,11 @@ __device__ __forceinline__ void pm2_rows_ring(const double *__restrict__ in, dou
         fixg(gS);
         const double fs0 = __dmul_rn(c.gC.x + gS.x, c.IS.x - c.IC.x), fs1 = __dmul_rn(c.gC.y + gS.y, c.IS.y - c.IC.y);  // Fy(i+1/2)
         const double ge = __shfl_down_sync(0xffffffffu, c.gC.x, 1);
-        const double g0 = c.gC.x + c.gC.y;                    // Fx(a+1/2) = g0 * d0, folded into the two FMAs below
+        double g0 = c.gC.x + c.gC.y;                          // Fx(a+1/2) = g0 * d0, folded into the two FMAs below
         double d0 = c.IC.y - c.IC.x;
         double fx1 = __dmul_rn(c.gC.y + ge, c.ICe - c.IC.y);  // Fx(a+3/2)
         if (EDGE) {
+            g0 = nofx0 ? 0.0 : g0;  // no flux across the right border; g of the column beyond it may be anything (NaN included)
             d0 = nofx0 ? 0.0 : d0;
             fx1 = bc1 ? 0.0 : fx1;
         }

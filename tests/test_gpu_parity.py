@@ -644,3 +644,49 @@ def test_async_mask_observer_abort(ctx):
     with pytest.raises(cv.ChanVeseError) as e:
         ctx.csv_run_masks(img, u0, cv.make_params(), lambda m, step: seen.append(step) or step == 3, tol=0.0, max_steps=50)
     assert "CALLBACK" in str(e.value) and seen == [1, 2, 3]
+
+
+# ---- BASELINE configs[4]: the image batch --------------------------------------------------------------------------------
+def test_config5_batch_subsample_against_oracle(ctx):
+    """64 of the 4096 images of C5 (512 x 512 RGB, PM 40 steps, CSV <= 50 steps with per-image early stop) as ONE batch
+    job against the oracle image by image: identical step counts, rel-L2(u) <= 1e-6, masks identical, PM planes within
+    one LSB.  The oracle runs the images on a thread pool (it is plain C behind ctypes: the GIL is released)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    c = synth.CONFIGS["C5"]
+    h, w, n, count = c["h"], c["w"], c["n"], 64
+    imgs = synth.batch_images(0, count, h, w)
+    prm = cv.make_params()
+    with cv.Batch(ctx, count, n, h, w) as b:
+        b.upload_images(imgs)
+        b.init_checkerboard()
+        assert b.perona_malik(**c["pm"]) == 40
+        steps, norms = b.csv_run(prm, tol=1e-3, max_steps=c["csv"]["max_steps"])
+        packed = b.masks_packed()
+        sample = {m: (b.download_image(m), b.download_levelset(m)) for m in range(count)}
+    u0 = co.levelset_checkerboard(h, w)
+
+    def ref(m):
+        pm, npm = co.perona_malik(list(imgs[m]), c["pm"]["K"], c["pm"]["L"], c["pm"]["T"])
+        u, s, nrm = co.csv_run(pm, u0, co.params(), 1e-3, c["csv"]["max_steps"])
+        return pm, u, s, nrm
+
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
+        refs = list(ex.map(ref, range(count)))
+    worst = 0.0
+    for m, (pm_ref, u_ref, s_ref, n_ref) in enumerate(refs):
+        pm_gpu, u_gpu = sample[m]
+        _planes_close(pm_gpu, pm_ref, frac=0.999)
+        # the CSV comparison must not inherit a PM tie (one LSB of one pixel): when the planes differ, the oracle is re-run on
+        # the GPU's own planes
+        if any(not np.array_equal(a, r) for a, r in zip(pm_gpu, pm_ref)):
+            u_ref, s_ref, n_ref = co.csv_run(pm_gpu, u0, co.params(), 1e-3, c["csv"]["max_steps"])
+        assert steps[m] == s_ref, (m, steps[m], s_ref)
+        r = rel_l2(u_gpu, u_ref)
+        worst = max(worst, r)
+        assert r <= TOL_U, (m, r)
+        mask = np.unpackbits(packed[m], axis=1)[:, :w]
+        assert np.array_equal(mask, co.mask(u_ref)), m
+        assert abs(norms[m] - n_ref) <= 1e-6 * max(n_ref, 1e-300)
+    assert steps.min() >= 1 and steps.max() <= c["csv"]["max_steps"]
+    print("C5 subsample: steps %d..%d, worst rel-L2 %.2e" % (steps.min(), steps.max(), worst))
