@@ -26,51 +26,71 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def _headers():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [HEADER, os.path.abspath(__file__)]
+STAMP = os.path.join(LIB_DIR, "build_stamp")
 
 
-def _stale():
-    if not os.path.exists(LIB_PATH):
+def _digest(extra_flags=()):
+    """Hash of everything the library is made of.  Staleness is decided by CONTENT, not by modification times: a
+    snapshot of the tree (gpurun, a checkout) copies files in arbitrary order, and several ranks import this module at the
+    same moment -- none of them may decide to rebuild a library that is already right."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + [HEADER, os.path.abspath(__file__)]:
+        path = f if os.path.isabs(f) else os.path.join(CSRC, f)
+        if os.path.isfile(path):
+            h.update(os.path.basename(path).encode())
+            with open(path, "rb") as fh:
+                h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + list(extra_flags)).encode())
+    return h.hexdigest()
+
+
+def _stale(lib_path=LIB_PATH, stamp=STAMP, extra_flags=()):
+    if not os.path.exists(lib_path) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [HEADER, os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(stamp) as fh:
+        return fh.read().strip() != _digest(extra_flags)
 
 
 def build(force=False, verbose=False, extra_flags=(), out=None):
-    """Compile the CUDA extension for sm_100a if it is missing or older than its sources: one object per .cu file
-    (compiled in parallel, only the stale ones), linked into one shared library.  `out`: alternative library path (tuning
-    variants built with extra flags; their objects are not cached)."""
+    """Compile the CUDA extension for sm_100a if it is missing or was built from other sources: one object per .cu file
+    (compiled in parallel), linked into one shared library that is moved into place atomically, under a file lock (ranks
+    of one job may call this concurrently).  `out`: alternative library path (tuning variants built with extra flags)."""
+    import fcntl
     extra_flags = list(extra_flags) + os.environ.get("CVB_EXTRA_NVCC_FLAGS", "").split()  # tuning sweeps only
-    variant = bool(extra_flags) or out is not None
     lib_path = out or LIB_PATH
-    if not force and not variant and not _stale():
+    stamp = STAMP if out is None else lib_path + ".stamp"
+    if not force and not _stale(lib_path, stamp, extra_flags):
         return lib_path
-    obj_dir = OBJ_DIR if not variant else lib_path + ".obj"
-    os.makedirs(obj_dir, exist_ok=True)
     os.makedirs(os.path.dirname(lib_path), exist_ok=True)
-    hdr_time = max(os.path.getmtime(h) for h in _headers())
-    jobs = []
-    for src in SOURCES:
-        sp, op = os.path.join(CSRC, src), os.path.join(obj_dir, src[:-3] + ".o")
-        if force or variant or not os.path.exists(op) or os.path.getmtime(op) < max(os.path.getmtime(sp), hdr_time):
-            jobs.append([_nvcc()] + NVCC_FLAGS + extra_flags + ["-c", sp, "-o", op])
-    # the image exports CC/CXX pointing at a relocated gcc; nvcc's default host compiler (g++ on PATH) is fine
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max(1, len(jobs))) as ex:
-        for cmd, res in zip(jobs, ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs)):
-            if verbose:
-                print(" ".join(cmd), file=sys.stderr)
-            if res.returncode != 0:
-                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", lib_path] + \
-           [os.path.join(obj_dir, src[:-3] + ".o") for src in SOURCES] + ["-ldl"]
-    if verbose:
-        print(" ".join(link), file=sys.stderr)
-    res = subprocess.run(link, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    with open(lib_path + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale(lib_path, stamp, extra_flags):  # another process built it while we waited
+            return lib_path
+        obj_dir = OBJ_DIR if out is None and not extra_flags else lib_path + ".obj"
+        os.makedirs(obj_dir, exist_ok=True)
+        jobs = [[_nvcc()] + NVCC_FLAGS + extra_flags + ["-c", os.path.join(CSRC, src), "-o", os.path.join(obj_dir, src[:-3] + ".o")]
+                for src in SOURCES]
+        # the image exports CC/CXX pointing at a relocated gcc; nvcc's default host compiler (g++ on PATH) is fine
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(jobs)) as ex:
+            for cmd, res in zip(jobs, ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs)):
+                if verbose:
+                    print(" ".join(cmd), file=sys.stderr)
+                if res.returncode != 0:
+                    raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        tmp = lib_path + ".tmp.%d" % os.getpid()
+        link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", tmp] + \
+               [os.path.join(obj_dir, src[:-3] + ".o") for src in SOURCES] + ["-ldl"]
+        if verbose:
+            print(" ".join(link), file=sys.stderr)
+        res = subprocess.run(link, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+        os.replace(tmp, lib_path)
+        with open(stamp + ".tmp", "w") as fh:
+            fh.write(_digest(extra_flags))
+        os.replace(stamp + ".tmp", stamp)
     return lib_path
 
 

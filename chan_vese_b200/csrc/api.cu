@@ -124,6 +124,9 @@ struct Job {
     CommBox *d_box = nullptr;
     CommView cv{};
     std::vector<void *> ipc_opened;
+#ifdef CSV_TMA
+    CUtensorMap tm_u[2], tm_img;
+#endif
     unsigned int pm_seq = 0;
     int pm_cur = -1;  // PM state buffer that holds the input of the last (quantising) step of the newest run; -1: none
 };
@@ -311,6 +314,32 @@ static int auto_seg_rows(int h, int w, int count, int /*nranks: deliberately unu
         if ((long long)count * ceil_div(h, s) * ncb >= 2LL * kSlots) return s;
     return 4;
 }
+// Segments per CTA of the production CSV kernel (Geom::seg_mult).  The segment length is the same for every GPU count (it
+// fixes the order of the sums); how many of them a CTA should march through is not: a job of many waves wants long row
+// loops (priming amortised), a slab of two or three waves wants short CTAs -- the last, partly filled wave and the drain
+// of a launch cost about one CTA's duration.  Model: CTAs of L = m * seg_rows rows (+ priming) run in ceil(waves)
+// generations, the last one weighted by how full it is.  CVB_SEG_MULT overrides.
+static int auto_seg_mult(int seg_rows, int nseg, int ncb, int count) {
+    if (const char *e = getenv("CVB_SEG_MULT"))
+        if (atoi(e) >= 1) return (seg_rows % 4 == 0 || atoi(e) == 1) ? atoi(e) : 1;
+    if (seg_rows % 4 != 0) return 1;  // the 4x unrolled row loop delivers a segment's sums between two groups of four rows
+    int best = 1;
+    double best_t = 1e300;
+    for (int m = 1; m <= 8 && m * seg_rows <= 256; ++m) {
+        const double ctas = (double)count * ceil_div(nseg, m) * ncb;
+        const double waves = ctas / kSlots;
+        const double len = (double)m * seg_rows + 3.5;
+        const double full = floor(waves), part = waves - full;
+        // a partly filled last generation runs faster than a full one (fewer warps share an SM), but not in proportion
+        const double t = (full + (part > 0 ? 0.35 + 0.65 * part : 0.0)) * len + 0.25 * len;
+        if (t < best_t * 0.995) {
+            best_t = t;
+            best = m;
+        }
+    }
+    return best;
+}
+
 // min_tail = HALO for the row slabs of a multi-rank run: the slab's last HALO rows should lie in ONE segment (they are
 // pushed to the neighbour by the CTAs of that segment; pm_push_boundary copes with a one-row last segment, but there is
 // no need to make one).  0 otherwise: whole images keep the plain choice.
@@ -532,6 +561,9 @@ static void job_free(Job *j) {
     if (j->h_state) cudaFreeHost(j->h_state);
 }
 
+#ifdef CSV_TMA
+static cvb_status job_make_tensor_maps(Job *j);
+#endif
 static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int w, int row_lo, int row_hi, bool slab,
                            cvb_precision prec) {
     if (!c) return CVB_ERR_INVALID_ARGUMENT;
@@ -561,14 +593,19 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
                     row_lo, row_hi, g.seg_rows);
     g.seg0 = row_lo / g.seg_rows;
     g.nseg = ceil_div(row_hi, g.seg_rows) - g.seg0;
+    g.seg_mult = auto_seg_mult(g.seg_rows, g.nseg, ceil_div(w, CSV_CB), count);
     g.ncb_csv = ceil_div(w, CSV_CB);
     g.ncb_pm = ceil_div(w, PM_CB);
     // PM has no reductions, so its segments need not follow the reduction groups: own wave-aware segment length
     g.pm_seg_rows = auto_pm_seg_rows(row_hi - row_lo, w, count * n, (slab && c->nranks > 1) ? HALO : 0);
+    if (const char *e = getenv("CVB_PM_SEG_ROWS"))  // tuning knob (PM results do not depend on the tiling)
+        if (atoi(e) >= 4) g.pm_seg_rows = atoi(e);
     g.pm_nseg = ceil_div(row_hi - row_lo, g.pm_seg_rows);
     // the fused two-step PM kernel: 56-column strips, 12 resident CTAs per SM, 4 priming rows more per segment
     g.ncb_pm2 = ceil_div(w, PM2_CB);
-    g.pm2_seg_rows = auto_pm_seg_rows(row_hi - row_lo, w, count * n, (slab && c->nranks > 1) ? HALO : 0, PM2_CB, 148 * 12, 7.5);
+    g.pm2_seg_rows = auto_pm_seg_rows(row_hi - row_lo, w, count * n, (slab && c->nranks > 1) ? HALO : 0, PM2_CB, kSlots, 7.5);
+    if (const char *e = getenv("CVB_PM2_SEG_ROWS"))
+        if (atoi(e) >= 4) g.pm2_seg_rows = atoi(e);
     g.pm2_nseg = ceil_div(row_hi - row_lo, g.pm2_seg_rows);
     g.plane_elems = (long long)g.rows_alloc * g.pitch;
     if ((long long)count * n * std::max(std::max(g.nseg, g.pm_nseg), g.pm2_nseg) * std::max(g.ncb_csv, g.ncb_pm2) > 0x7fffffffLL)
@@ -608,6 +645,9 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     // a reduction group of more than 128 partial vectors is summed per segment first; keyed to the GLOBAL geometry, so
     // every slab of an image takes the same decision
     j->seg_level = ((long long)ceil_div(g.nseg_global, NGROUPS) * g.ncb_csv > 128) ? 1 : 0;
+#ifdef CSV_TMA
+    TRY(job_make_tensor_maps(j));
+#endif
     CU(c, cudaMallocHost(&j->h_state, 2 * (size_t)count * sizeof(CsvState)));
     CU(c, cudaMemsetAsync(j->d_img, 0, (size_t)count * n * pe + tail, c->stream));
     CU(c, cudaMemsetAsync(j->d_u[0], 0, ((size_t)count * pe + tail) * esz(j), c->stream));
@@ -618,8 +658,47 @@ static cvb_status job_init(Job *j, cvb_context *c, int count, int n, int h, int 
     return CVB_OK;
 }
 
+#ifdef CSV_TMA
+// Tensor maps of the job's level-set buffers and image planes (build variant CSV_TMA, csv_kernels.cu).
+static cvb_status job_make_tensor_maps(Job *j) {
+    cvb_context *c = j->ctx;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, CVB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    const Geom &g = j->g;
+    const cuuint32_t one[3] = {1, 1, 1};
+    if (!is_f32(j))
+        for (int b = 0; b < 2; ++b) {
+            const cuuint64_t dim[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.count * g.rows_alloc + TAIL_ROWS};
+            const cuuint64_t str[1] = {(cuuint64_t)g.pitch * sizeof(double)};
+            const cuuint32_t box[2] = {66, 4};
+            const CUresult r = ((encode_fn)fn)(&j->tm_u[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, j->d_u[b], dim, str, box, one,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(c, CVB_ERR_CUDA, "cuTensorMapEncodeTiled(u) failed: %d", (int)r);
+        }
+    const cuuint64_t dim[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows_alloc, (cuuint64_t)g.count * g.nch};
+    const cuuint64_t str[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.plane_elems};
+    const cuuint32_t box[3] = {80, 4, (cuuint32_t)g.nch};
+    const CUresult r = ((encode_fn)fn)(&j->tm_img, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, j->d_img, dim, str, box, one,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, CVB_ERR_CUDA, "cuTensorMapEncodeTiled(image) failed: %d", (int)r);
+    return CVB_OK;
+}
+#endif
+
 static void fill_args(const Job *j, const cvb_csv_params *p, double tol, CsvArgs &A) {
     memset(&A, 0, sizeof A);
+#ifdef CSV_TMA
+    A.tm_u[0] = j->tm_u[0];
+    A.tm_u[1] = j->tm_u[1];
+    A.tm_img = j->tm_img;
+#endif
     A.u[0] = j->d_u[0];
     A.u[1] = j->d_u[1];
     A.img = j->d_img;

@@ -14,6 +14,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef CSV_TMA  // build variant: the CSV row ring is filled by the tensor memory accelerator (csv_kernels.cu)
+#include <cuda.h>
+#endif
 
 namespace cvb {
 
@@ -44,7 +47,10 @@ struct Geom {
     int rows_alloc;      // row_hi - row_lo + 2*HALO
     int nch;             // channels
     int count;           // images in the job
-    int seg_rows;        // rows per segment; segments start at global rows that are multiples of it
+    int seg_rows;        // rows per segment; segments start at global rows that are multiples of it.  A segment is the
+                         // unit of the fused sums (one partial vector per segment and strip): it fixes their order.
+    int seg_mult;        // consecutive segments one CTA of the production CSV kernel marches through (it delivers one
+                         // partial vector per segment, so the sums -- and the results -- do not depend on it)
     int nseg;            // segments in [row_lo, row_hi)
     int seg0;            // global index of the first local segment (row_lo / seg_rows)
     int nseg_global;     // segments of the whole image
@@ -119,6 +125,11 @@ struct CsvArgs {
     int group_lo, group_hi; // groups owned by this rank
     Geom g;
     CommView cv;
+#ifdef CSV_TMA
+    // tensor maps of the level-set buffers (2-D: pitch x all rows of all planes) and of the image (3-D: pitch x rows x planes)
+    alignas(64) CUtensorMap tm_u[2];
+    alignas(64) CUtensorMap tm_img;
+#endif
 };
 
 struct PmArgs {

@@ -13,6 +13,7 @@
 // HBM -> shared memory through a cp.async ring 7 rows ahead of the row being computed, east / west neighbours are
 // read from the ring.  Generic path (strict math, curvature-only mode): explicit clamps, register prefetch CSV_D rows
 // ahead and L2 prefetch CSV_PF rows ahead.
+#include <limits.h>
 #include <string.h>
 
 #include "async_copy.cuh"
@@ -121,11 +122,44 @@ constexpr int RING_BYTES = RING_NS * RING_SLOT;
 static_assert(RING_IMG + 80 * MAX_CH <= RING_SLOT, "slot too small");
 static_assert(RING_NS - 1 <= TAIL_ROWS, "tail padding too small for the ring");
 
+// A CTA that marches through several segments (Geom::seg_mult) delivers the sums of a finished segment from inside its
+// row loop: rare (once per seg_rows rows), out of line so that the hot loop's register allocation does not see it.
+// sums of lane 0 (a halo lane) are dropped, as at the end of the row loop.
+struct SegCursor {
+    const CsvArgs *A;
+    int img, seg, cb;   // seg: the local segment the rows being computed belong to
+    int next;           // first row (relative to the CTA's first row) of the next segment; INT_MAX: no further segment
+};
+template <int NCH>
+__device__ __noinline__ void csv_flush_segment(const CsvArgs &A, int img, int seg, int cb, double a, double s, double i0, double i1,
+                                               double i2) {
+    double acc[NACC];
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
+    if (threadIdx.x & 31) {
+        acc[ACC_A] = a;
+        acc[ACC_SQ] = s;
+        acc[ACC_IA] = i0;
+        if (NCH > 1) acc[ACC_IA + 1] = i1;
+        if (NCH > 2) acc[ACC_IA + 2] = i2;
+    }
+    finish_tile<NCH, false>(A, img, seg, cb, A.g.ncb_csv, acc, 0, false);
+}
+#define CSV_SEGMENT_BOUNDARY(r)                                                                                         \
+    if ((r) == cur.next) {                                                                                             \
+        csv_flush_segment<NCH>(*cur.A, cur.img, cur.seg, cur.cb, accA, accS, accI[0], NCH > 1 ? accI[NCH > 1 ? 1 : 0] : 0.0, \
+                               NCH > 2 ? accI[NCH > 2 ? 2 : 0] : 0.0);                                                  \
+        ++cur.seg;                                                                                                     \
+        cur.next += G.seg_rows;                                                                                        \
+        accA = accS = 0.0;                                                                                             \
+        _Pragma("unroll") for (int c = 0; c < NCH; ++c) accI[c] = 0.0;                                                 \
+    }
+
 template <int NCH, bool EDGE, bool LINEAR>
 __device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, double *__restrict__ uout,
                                               const uint8_t *__restrict__ im, const Geom &G, const StepCoef<NCH> &K,
                                               const double2 *s_tab, unsigned char *ring, int ra, int rb, int cs, int lane,
-                                              double (&acc)[NACC]) {
+                                              double (&acc)[NACC], SegCursor &cur) {
     const int w = G.w;
     const int a = cs - 2 + 2 * lane;
     const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
@@ -223,15 +257,8 @@ __device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, do
         double I0[NCH], I1[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-#ifdef CSV_I256
-            // 256 + I, exact, built in the integer pipe (the byte goes to mantissa bits 44..51 of 2^8): no FP64
-            // conversion; the coefficients and the sums below are written for I' = I + 256 (StepCoef, end of the loop)
-            I0[c] = __hiloint2double(0x40700000 | ((Ib[c] & 0xffu) << 12), 0);
-            I1[c] = __hiloint2double(0x40700000 | ((Ib[c] << 4) & 0xff000u), 0);
-#else
             I0[c] = u8_to_double(Ib[c] & 0xffu);
             I1[c] = u8_to_double(Ib[c] >> 8);
-#endif
         }
         double t0 = K.q0, t1 = K.q0;
 #pragma unroll
@@ -296,6 +323,7 @@ __device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, do
     unsigned int tog = 0;  // offset of slot 0 or slot 4: the slot of the first row of a group of four
 #pragma unroll 1
     for (; r + 4 <= n; r += 4) {
+        CSV_SEGMENT_BOUNDARY(r)  // seg_rows is a multiple of 4 whenever seg_mult > 1
         const unsigned int t2 = tog ^ (4 * RING_SLOT);
         row(t2 + 3 * RING_SLOT, tog, tog + RING_SLOT);
         row(tog, tog + RING_SLOT, tog + 2 * RING_SLOT);
@@ -303,6 +331,7 @@ __device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, do
         row(tog + 2 * RING_SLOT, tog + 3 * RING_SLOT, t2);
         tog = t2;
     }
+    CSV_SEGMENT_BOUNDARY(r)
 #pragma unroll 1
     for (; r < n; ++r) {
         const unsigned int k = (unsigned int)r;
@@ -313,26 +342,260 @@ __device__ __forceinline__ void csv_rows_ring(const double *__restrict__ uin, do
         acc[ACC_A] = accA;
         acc[ACC_SQ] = accS;
 #pragma unroll
-#ifdef CSV_I256
-        for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = fma(-256.0, accA, accI[c]);  // sum (I+256) a - 256 sum a
-#else
         for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = accI[c];
-#endif
     }
 }
+
+#ifdef CSV_TMA
+// ---- build variant: the same row loop fed by the tensor memory accelerator ---------------------------------------------
+// One cp.async.bulk.tensor.2d per TMA_R-row x 66-column tile of u and one .3d per tile of the image channels, issued by
+// one lane, completion on an mbarrier per stage; TMA_NST stages.  A tile is exactly the four rows of one unrolled loop
+// iteration, so per iteration the warp executes one barrier wait and (lane 0) one expect_tx + two bulk copies instead of
+// 4 x (2 LDGSTS + commit + wait) and their address arithmetic.  Boxes that reach outside the tensor (strips at the left /
+// right border, rows past the last plane) are zero-filled by the hardware.
+constexpr int TMA_R = 4;
+constexpr int TMA_NST = 3;
+constexpr int TMA_UROW = 33 * 16;                        // 66 doubles
+constexpr int TMA_UB = (TMA_R * TMA_UROW + 127) / 128 * 128;
+constexpr int TMA_IROW = 80;
+constexpr int TMA_IB = (MAX_CH * TMA_R * TMA_IROW + 127) / 128 * 128;
+constexpr int TMA_STAGE = TMA_UB + TMA_IB;
+constexpr int TMA_LEAD = 128;                            // mbarriers + the 8 bytes lane 0 reads west of a tile
+constexpr int TMA_BYTES = TMA_LEAD + TMA_NST * TMA_STAGE;
+
+__device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "CVB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra CVB_DONE;\n\t"
+        "bra CVB_WAIT;\n\t"
+        "CVB_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned int dst, const CUtensorMap *m, unsigned int bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(m), "r"(bar), "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned int dst, const CUtensorMap *m, unsigned int bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(m), "r"(bar), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+
+template <int NCH, bool EDGE, bool LINEAR>
+__device__ __forceinline__ void csv_rows_tma(const double *__restrict__ uin, double *__restrict__ uout, const CUtensorMap *tm_u,
+                                             const CUtensorMap *tm_img, int img, const Geom &G, const StepCoef<NCH> &K,
+                                             const double2 *s_tab, unsigned char *ring, int ra, int rb, int cs, int lane,
+                                             double (&acc)[NACC], SegCursor &cur) {
+    const int w = G.w;
+    const int a = cs - 2 + 2 * lane;
+    const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
+    const bool v0 = lane >= 1 && (!EDGE || a < w), v1 = lane >= 1 && (!EDGE || a + 1 < w);
+    const unsigned int p2 = (unsigned int)G.pitch >> 1;
+    unsigned int o = (unsigned int)(ra - G.row_lo + HALO) * p2 + (unsigned int)(a >> 1);
+    const double2 *bu = reinterpret_cast<const double2 *>(uin);
+    double2 *bo = reinterpret_cast<double2 *>(uout);
+    const int s_al = (cs - 2) & ~15;  // first column of the image box
+    const int dsh = (cs - 2) - s_al;
+    const bool ok1 = !EDGE || (a >= 0 && a < G.pitch);
+    const int n = rb - ra;
+    const int ntiles = (n + 1 + TMA_R - 1) / TMA_R;  // rows ra .. rb (the row below the segment is the last south row)
+    const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring);
+    const int urow0 = img * G.rows_alloc + (ra - G.row_lo + HALO), irow0 = ra - G.row_lo + HALO, z0 = img * G.nch;
+    constexpr unsigned int kBytes = TMA_R * TMA_UROW + NCH * TMA_R * TMA_IROW;
+    auto issue_tile = [&](int t) {  // one lane
+        const unsigned int st = ring_s + TMA_LEAD + (unsigned int)(t % TMA_NST) * TMA_STAGE, bar = ring_s + 8u * (unsigned int)(t % TMA_NST);
+        mbar_expect_tx(bar, kBytes);
+        tma_load_2d(st, tm_u, bar, cs - 2, urow0 + TMA_R * t);
+        tma_load_3d(st + TMA_UB, tm_img, bar, s_al, irow0 + TMA_R * t, z0);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < TMA_NST; ++k) mbar_init(ring_s + 8u * k, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < TMA_NST; ++k)
+            if (k < ntiles) issue_tile(k);
+    }
+    // rows ra-2, ra-1 (own columns only) straight from global memory
+    const double2 R0 = ok1 ? __ldg(bu + o - 2 * p2) : make_double2(0.0, 0.0);
+    const double2 R1 = ok1 ? __ldg(bu + o - p2) : make_double2(0.0, 0.0);
+    const unsigned char *mu = ring + TMA_LEAD + 16 * lane;                   // + stage + row * TMA_UROW: own chunk
+    const unsigned char *mi = ring + TMA_LEAD + TMA_UB + dsh + 2 * lane;     // + stage + c * TMA_R * TMA_IROW + row * TMA_IROW
+    mbar_wait(ring_s, 0u);  // tile 0
+    double2 C = *reinterpret_cast<const double2 *>(mu);
+    double CW = *reinterpret_cast<const double *>(mu - 8);
+    double CE = *reinterpret_cast<const double *>(mu + 16);
+    double dN0 = C.x - R1.x, dN1 = C.y - R1.y;
+    double nyp0 = normal_component<false>(dN0, dN0 + (R1.x - R0.x));
+    double nyp1 = normal_component<false>(dN1, dN1 + (R1.y - R0.y));
+    if (ra == 0) {  // see csv_rows_ring
+        const double2 q = *reinterpret_cast<const double2 *>(mu + TMA_UROW);
+        nyp0 = normal_component<false>(q.x - C.x, (q.x - C.x) + dN0);
+        nyp1 = normal_component<false>(q.y - C.y, (q.y - C.y) + dN1);
+    }
+    double accA = 0.0, accS = 0.0, accI[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) accI[c] = 0.0;
+
+    // one row: pu = own chunk of row i+1, pi = own image bytes of row i (channel 0; channel stride TMA_R * TMA_IROW)
+    auto row = [&](const unsigned char *pu, const unsigned char *pi) {
+        const double2 S = *reinterpret_cast<const double2 *>(pu);
+        const double SW = *reinterpret_cast<const double *>(pu - 8);
+        const double SE = *reinterpret_cast<const double *>(pu + 16);
+        unsigned int Ib[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) Ib[c] = *reinterpret_cast<const unsigned short *>(pi + c * (TMA_R * TMA_IROW));
+        const double upy0 = S.x - C.x, upy1 = S.y - C.y;
+        const double ny0 = normal_component<false>(upy0, upy0 + dN0);
+        const double ny1 = normal_component<false>(upy1, upy1 + dN1);
+        double Wn = CW, E2 = CE, E0 = C.y;
+        if (EDGE) {
+            Wn = first ? C.x : Wn;
+            E0 = last0 ? C.x : C.y;
+            E2 = last1 ? C.y : E2;
+        }
+        const double nx0 = normal_component<false>(E0 - C.x, E0 - Wn);
+        const double nx1 = normal_component<false>(E2 - C.y, E2 - C.x);
+        const double nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
+        double kx0 = nx0 - nxw;
+        if (EDGE) kx0 = first ? 0.0 : kx0;
+        const double kap0 = kx0 + (ny0 - nyp0);
+        const double kap1 = (nx1 - nx0) + (ny1 - nyp1);
+        double I0[NCH], I1[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            I0[c] = u8_to_double(Ib[c] & 0xffu);
+            I1[c] = u8_to_double(Ib[c] >> 8);
+        }
+        double t0 = K.q0, t1 = K.q0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            if (LINEAR) {
+                t0 = fma(K.cB[c], I0[c], t0);
+                t1 = fma(K.cB[c], I1[c], t1);
+            } else {
+                t0 = fma(fma(K.cA[c], I0[c], K.cB[c]), I0[c], t0);
+                t1 = fma(fma(K.cA[c], I1[c], K.cB[c]), I1[c], t1);
+            }
+        }
+        t0 = fma(kap0, K.alphap, t0);
+        t1 = fma(kap1, K.alphap, t1);
+        const double s0 = fma(C.x, C.x, K.eps2), s1 = fma(C.y, C.y, K.eps2);
+        const double rs = fast_rcp(s0 * s1);
+        const double du0 = t0 * (rs * s1);
+        const double du1 = t1 * (rs * s0);
+        const double un0 = C.x + du0, un1 = C.y + du1;
+        double2 *po = bo + o;
+        if (EDGE) {
+            if (v1)
+                *po = make_double2(un0, un1);
+            else if (v0)
+                *reinterpret_cast<double *>(po) = un0;
+        } else if (lane) {
+            *po = make_double2(un0, un1);
+        }
+        o += p2;
+        double a0, a1;
+        atan_over_pi2(un0 * K.inv_eps, un1 * K.inv_eps, s_tab, a0, a1);
+        double dq0 = du0, dq1 = du1;
+        if (EDGE) {
+            a0 = v0 ? a0 : 0.0;
+            a1 = v1 ? a1 : 0.0;
+            dq0 = v0 ? du0 : 0.0;
+            dq1 = v1 ? du1 : 0.0;
+        }
+        accA += a0;
+        accA += a1;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            accI[c] = fma(I0[c], a0, accI[c]);
+            accI[c] = fma(I1[c], a1, accI[c]);
+        }
+        accS = fma(dq0, dq0, accS);
+        accS = fma(dq1, dq1, accS);
+        dN0 = upy0;
+        dN1 = upy1;
+        nyp0 = ny0;
+        nyp1 = ny1;
+        C = S;
+        CW = SW;
+        CE = SE;
+    };
+
+    int r = 0, t = 0;
+    unsigned int sc = 0, sn = TMA_STAGE;  // byte offsets of the stages of tile t and tile t+1
+    unsigned int par_next = 0;            // parity of the next wait on tile t+1's stage
+#pragma unroll 1
+    for (; r + TMA_R <= n; r += TMA_R, ++t) {
+        CSV_SEGMENT_BOUNDARY(r)
+        // tile t+1 (its first row is the south row of this tile's last row) -- parity of its stage's (t+1)/NST-th completion
+        par_next = (unsigned int)(((t + 1) / TMA_NST) & 1);
+        mbar_wait(ring_s + 8u * (unsigned int)((t + 1) % TMA_NST), par_next);
+        row(mu + sc + TMA_UROW, mi + sc);
+        row(mu + sc + 2 * TMA_UROW, mi + sc + TMA_IROW);
+        row(mu + sc + 3 * TMA_UROW, mi + sc + 2 * TMA_IROW);
+        row(mu + sn, mi + sc + 3 * TMA_IROW);
+        __syncwarp();  // every lane has read tile t: its stage may be refilled
+        if (lane == 0 && t + TMA_NST < ntiles) issue_tile(t + TMA_NST);
+        sc = sn;
+        sn = (sn == (TMA_NST - 1) * TMA_STAGE) ? 0u : sn + TMA_STAGE;
+    }
+    // tail (< TMA_R rows): tile t has been waited for; the south row of local row 3 of a tile lives in tile t+1
+    CSV_SEGMENT_BOUNDARY(r)
+#pragma unroll 1
+    for (int k = 0; r < n; ++r, ++k) {
+        if (k == TMA_R - 1) mbar_wait(ring_s + 8u * (unsigned int)((t + 1) % TMA_NST), (unsigned int)(((t + 1) / TMA_NST) & 1));
+        const unsigned char *pu = (k == TMA_R - 1) ? mu + sn : mu + sc + (k + 1) * TMA_UROW;
+        row(pu, mi + sc + k * TMA_IROW);
+    }
+    // every issued tile has been waited for unless the tail ended before its last tile was needed: drain
+#pragma unroll 1
+    for (int q = t + 1; q < ntiles; ++q) mbar_wait(ring_s + 8u * (unsigned int)(q % TMA_NST), (unsigned int)((q / TMA_NST) & 1));
+    if (lane) {
+        acc[ACC_A] = accA;
+        acc[ACC_SQ] = accS;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = accI[c];
+    }
+}
+#endif  // CSV_TMA
 
 template <int NCH, bool STRICT, int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(const __grid_constant__ CsvArgs A) {
     const Geom &G = A.g;
     __shared__ double2 s_tab[ATAN_TAB_N];  // {atan(c_q)/pi, c_q}
+#ifdef CSV_TMA
+    __shared__ __align__(128) unsigned char s_ring[(MODE == MODE_STEP && !STRICT) ? TMA_BYTES : 16];
+#else
     __shared__ __align__(16) unsigned char s_ring[(MODE == MODE_STEP && !STRICT) ? RING_BYTES : 16];
+#endif
     const int lane = threadIdx.x;
     constexpr int warp = 0;
     int bid = blockIdx.x;
     const int cb = bid % G.ncb_csv;
     bid /= G.ncb_csv;
-    const int seg = bid % G.nseg;
-    const int img = bid / G.nseg;
+    // the production kernel marches through seg_mult consecutive segments per CTA (long row loops amortise the priming;
+    // how long is best depends on how many waves the job has, i.e. on the GPU count) and delivers one partial vector per
+    // segment; the other instantiations take one segment per CTA
+    const int mult = (MODE == MODE_STEP && !STRICT) ? G.seg_mult : 1;
+    const int nsup = (G.nseg + mult - 1) / mult;
+    const int seg = (bid % nsup) * mult;              // first local segment
+    const int seg_end = min(seg + mult, G.nseg);      // one past the last
+    const int img = bid / nsup;
     CsvState *st = A.state + img;
 #pragma unroll
     for (int q = 0; q < ATAN_TAB_N; q += 32) s_tab[q + lane] = make_double2(A.atan_tab[q + lane], atan_centre(q + lane));
@@ -353,7 +616,13 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
 
     const int gseg = G.seg0 + seg;
     const int ra = max(gseg * G.seg_rows, G.row_lo);
-    const int rb = min((gseg + 1) * G.seg_rows, G.row_hi);
+    const int rb = min((G.seg0 + seg_end) * G.seg_rows, G.row_hi);
+    SegCursor cur;
+    cur.A = &A;
+    cur.img = img;
+    cur.seg = seg;
+    cur.cb = cb;
+    cur.next = (seg_end - seg > 1) ? (gseg + 1) * G.seg_rows - ra : INT_MAX;
     const int cs = cb * CSV_CB + warp * CSV_STRIP_OWN;
     const int a = cs - 2 + 2 * lane;  // this lane's columns: a, a+1
     const int w = G.w, h = G.h;
@@ -402,36 +671,31 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
 #endif
     const double q0 = K.q0, alphap = K.alphap, eps2 = K.eps2;
     const double *cA = K.cA, *cB = K.cB;
-#ifdef CSV_I256
-    // the ring paths evaluate the data term in I' = I + 256:  A I^2 + B I + q0 = A I'^2 + (B - 512 A) I' + (q0 + 65536 A - 256 B)
-    StepCoef<NCH> K2 = K;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-        K2.cB[k] = fma(-512.0, K.cA[k], K.cB[k]);
-        K2.q0 += fma(65536.0, K.cA[k], -256.0 * K.cB[k]);
-    }
-#else
     const StepCoef<NCH> &K2 = K;
-#endif
 
     double acc[NACC];
 #pragma unroll
     for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
 
+#ifdef CSV_TMA
+#define CSV_ROWS(E, L) csv_rows_tma<NCH, E, L>(uin, uout, &A.tm_u[par], &A.tm_img, img, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc, cur)
+#else
+#define CSV_ROWS(E, L) csv_rows_ring<NCH, E, L>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc, cur)
+#endif
     // CTAs whose stencils stay inside the image take the fast path (all but the outermost ring)
     // (image top and bottom included: the halo rows there hold copies of the border rows, see replicate_border_rows)
     const bool interior = !STRICT && MODE == MODE_STEP && cb > 0 && (cb + 1) * CSV_CB < w;
     const bool edge_fast = !STRICT && MODE == MODE_STEP && !interior && cs < w;
     if (interior) {
         if (K.linear)
-            csv_rows_ring<NCH, false, true>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc);
+            CSV_ROWS(false, true);
         else
-            csv_rows_ring<NCH, false, false>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc);
+            CSV_ROWS(false, false);
     } else if (edge_fast) {
         if (K.linear)
-            csv_rows_ring<NCH, true, true>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc);
+            CSV_ROWS(true, true);
         else
-            csv_rows_ring<NCH, true, false>(uin, uout, im, G, K2, s_tab, s_ring, ra, rb, cs, lane, acc);
+            CSV_ROWS(true, false);
     } else if (cs < w) {
         const int nk = rb - ra + 3;  // streamed rows ra-2 .. rb
         double2 pq[CSV_D];
@@ -603,7 +867,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
         bool pushed = false;
         if (A.cv.p2p && cs < w && colok && (ra < G.row_lo + HALO || rb > G.row_hi - HALO))
             pushed = push_boundary_rows(A, uout, par ^ 1, ra, rb, a, lane);
-        finish_tile<NCH, false>(A, img, seg, cb, G.ncb_csv, acc, 0, pushed);
+        finish_tile<NCH, false>(A, img, cur.seg, cb, G.ncb_csv, acc, 0, pushed);  // the last (or only) segment of this CTA
     }
 }
 
@@ -798,7 +1062,8 @@ cudaError_t launch_replicate_halo(void *base, size_t plane_bytes, size_t row_byt
 template <int NCH>
 static cudaError_t launch_step_n(const CsvArgs &A, bool strict, int mode, cudaStream_t s) {
     const Geom &G = A.g;
-    const unsigned int grid = (unsigned int)((size_t)G.count * G.nseg * G.ncb_csv);
+    const int mult = (mode == MODE_STEP && !strict) ? G.seg_mult : 1;
+    const unsigned int grid = (unsigned int)((size_t)G.count * ceil_div(G.nseg, mult) * G.ncb_csv);
     if (mode == MODE_KAPPA) {
         if (strict)
             csv_step_kernel<NCH, true, MODE_KAPPA><<<grid, CTA_THREADS, 0, s>>>(A);

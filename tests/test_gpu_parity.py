@@ -690,3 +690,32 @@ def test_config5_batch_subsample_against_oracle(ctx):
         assert abs(norms[m] - n_ref) <= 1e-6 * max(n_ref, 1e-300)
     assert steps.min() >= 1 and steps.max() <= c["csv"]["max_steps"]
     print("C5 subsample: steps %d..%d, worst rel-L2 %.2e" % (steps.min(), steps.max(), worst))
+
+
+# ---- the tiling of a job: segments fix the order of the sums, segments per CTA must not matter ---------------------
+def test_results_do_not_depend_on_segments_per_cta(ctx):
+    """Geom::seg_mult (how many segments one CTA marches through -- chosen per GPU count for speed) changes neither the
+    level set, nor the step at which the tolerance ends the run, nor the norm: bit for bit."""
+    import os
+    h, w = 203, 330
+    img = synth.seastar(h, w, seed=9)
+    u0 = cv.levelset_checkerboard(h, w)
+    prm = cv.make_params(lambda1=[1.0, 0.7, 1.3])
+    out = []
+    ctx.set_tile_rows(8)
+    try:
+        for mult in ("1", "2", "3", "7"):
+            os.environ["CVB_SEG_MULT"] = mult
+            with cv.Session(ctx, 3, h, w) as s:
+                s.upload_image(img)
+                s.upload_levelset(u0)
+                steps, norm = s.csv_run(prm, tol=0.02, max_steps=60)
+                out.append((s.download_levelset(), steps, norm))
+    finally:
+        os.environ.pop("CVB_SEG_MULT", None)
+        ctx.set_tile_rows(0)
+    assert 1 < out[0][1] < 60  # the tolerance ended the run
+    for u, steps, norm in out[1:]:
+        assert steps == out[0][1] and norm == out[0][2] and np.array_equal(u, out[0][0])
+    ref, rs, _ = co.csv_run(img, u0, co.params(lambda1=[1.0, 0.7, 1.3]), 0.02, 60)
+    assert rs == out[0][1] and rel_l2(out[0][0], ref) < TOL_U
