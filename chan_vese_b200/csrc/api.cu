@@ -323,6 +323,10 @@ static int auto_seg_mult(int seg_rows, int nseg, int ncb, int count) {
     if (const char *e = getenv("CVB_SEG_MULT"))
         if (atoi(e) >= 1) return (seg_rows % 4 == 0 || atoi(e) == 1) ? atoi(e) : 1;
     if (seg_rows % 4 != 0) return 1;  // the 4x unrolled row loop delivers a segment's sums between two groups of four rows
+    // Measured (profiles/README.md, r2g): at 16384^2 on 8 GPUs tiles of 40, 64 and 123 rows give the same csv_step time
+    // within 1 % -- the shorter tail of short CTAs and their extra priming cancel -- so the automatic tile length already
+    // serves every GPU count and one segment per CTA stays the default; the model below is used for explicit small tiles.
+    if (seg_rows >= 48) return 1;
     int best = 1;
     double best_t = 1e300;
     for (int m = 1; m <= 8 && m * seg_rows <= 256; ++m) {

@@ -146,7 +146,7 @@ __device__ __noinline__ void csv_flush_segment(const CsvArgs &A, int img, int se
     finish_tile<NCH, false>(A, img, seg, cb, A.g.ncb_csv, acc, 0, false);
 }
 #define CSV_SEGMENT_BOUNDARY(r)                                                                                         \
-    if ((r) == cur.next) {                                                                                             \
+    if ((r) == cur.next && (r) < n) { /* the sums of the CTA's LAST segment are delivered after the loop */            \
         csv_flush_segment<NCH>(*cur.A, cur.img, cur.seg, cur.cb, accA, accS, accI[0], NCH > 1 ? accI[NCH > 1 ? 1 : 0] : 0.0, \
                                NCH > 2 ? accI[NCH > 2 ? 2 : 0] : 0.0);                                                  \
         ++cur.seg;                                                                                                     \
@@ -593,7 +593,12 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
     // segment; the other instantiations take one segment per CTA
     const int mult = (MODE == MODE_STEP && !STRICT) ? G.seg_mult : 1;
     const int nsup = (G.nseg + mult - 1) / mult;
-    const int seg = (bid % nsup) * mult;              // first local segment
+    // row slabs: the CTAs of the LAST segments go first (then the first ones): they store the slab's bottom rows into the
+    // lower neighbour's halo and fence at system scope -- in the first wave that is hidden behind the bulk of the launch,
+    // in the last one it would sit in the tail that every rank waits for
+    int sup = bid % nsup;
+    if (MODE == MODE_STEP && A.cv.p2p && nsup > 1) sup = (sup == 0) ? nsup - 1 : sup - 1;
+    const int seg = sup * mult;                       // first local segment
     const int seg_end = min(seg + mult, G.nseg);      // one past the last
     const int img = bid / nsup;
     CsvState *st = A.state + img;

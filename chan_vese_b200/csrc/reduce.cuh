@@ -225,29 +225,36 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
         csv_fold(A, img, final_mode, 0u);
         return;
     }
-    // slab session (count == 1): this rank's group sums go to every peer, then the arrival flags
+    // slab session (count == 1): this rank's group sums go to every peer (the warp copies them together: one L2 read per
+    // value, nranks - 1 posted stores over NVLink), then lane p raises peer p's flag with st.release.sys -- the release,
+    // after the warp barrier, orders every lane's stores before the flag: ONE system-scope round trip, no separate fence.
     const size_t first = (size_t)A.group_lo * G.count * NACC;
-    const int nval = (A.group_hi - A.group_lo) * G.count * NACC;
+    const int nval2 = (A.group_hi - A.group_lo) * G.count * NACC / 2;  // in double2 (NACC is even)
     const size_t poff = (size_t)(prod & 1u) * NGROUPS * G.count * NACC + first;
-    for (int i = lane; i < nval; i += 32) {  // one load, nranks - 1 remote stores (posted writes over NVLink)
-        const double v = ld_cg(gbase + first + i);
+    const double2 *src = reinterpret_cast<const double2 *>(gbase + first);
+    for (int i = lane; i < nval2; i += 64) {
+        const bool two = i + 32 < nval2;
+        const double2 v0 = __ldcg(src + i), v1 = two ? __ldcg(src + i + 32) : make_double2(0.0, 0.0);
         for (int p = 0; p < A.cv.nranks; ++p)
-            if (p != A.cv.rank) A.cv.peer_group[p][poff + i] = v;
+            if (p != A.cv.rank) {
+                double2 *dst = reinterpret_cast<double2 *>(A.cv.peer_group[p] + poff);
+                dst[i] = v0;
+                if (two) dst[i + 32] = v1;
+            }
     }
-    __threadfence_system();
-    __syncwarp();
     if (lane == 0) {
         A.cv.box->pending_mode = final_mode;
-        __threadfence();
         *reinterpret_cast<volatile unsigned int *>(&A.cv.box->produced) = prod;
     }
-    if (lane < A.cv.nranks) st_release_sys(&A.cv.peer_box[lane]->arrive[A.cv.rank], prod);
-    // ... and fold right here, in the tail of the same launch: this one warp waits until every rank has arrived (the
-    // other SMs of this GPU are idle by now; the peers only need THEIR OWN launch to finish, so nobody waits in a
-    // circle), then adds the group sums -- the same numbers in the same order on every rank.  No extra launch per step.
-    if (lane < A.cv.nranks) spin_until(&A.cv.box->arrive[lane], prod, A.cv.box);
     __syncwarp();
-    __threadfence_system();
+    if (lane < A.cv.nranks) {
+        st_release_sys(&A.cv.peer_box[lane]->arrive[A.cv.rank], prod);
+        // ... and fold right here, in the tail of the same launch: wait until every rank has arrived (the other SMs of
+        // this GPU are idle by now; the peers only need THEIR OWN launch to finish, so nobody waits in a circle), then
+        // add the group sums -- the same numbers in the same order on every rank.  No extra launch per step.
+        spin_until(&A.cv.box->arrive[lane], prod, A.cv.box);
+    }
+    __syncwarp();  // lane p has acquired peer p's flag: with the warp barrier every lane may read every peer's sums
     csv_fold(A, 0, final_mode, prod);
     if (lane == 0) A.cv.box->finalized = prod;
 }
