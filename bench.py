@@ -453,6 +453,7 @@ def run_slabs(args):
     parts.append(crc_of(mask_view))
     all_parts = h.gather(parts)
     all_digest = h.gather((digest_resident, (last["n_csv"], float(last["norm"]).hex())))
+    all_wait = h.gather((st.get("peer_wait_ms", 0.0), st.get("peer_waits", 0), st["csv_ms"], st["csv_step_launches"]))
     if rank != 0:
         sess.close()
         h.close()
@@ -493,6 +494,8 @@ def run_slabs(args):
                                 "ms_per_launch": pm_launch_ms, "ms_per_step_equivalent": pm_launch_ms / pm_steps_per_launch,
                                 "GBps": pm_gbs, "frac": pm_gbs / peak,
                                 "pixel_iters_per_s": pm_steps_per_launch * rows * W / (pm_launch_ms * 1e-3)},
+                    "per_rank": [{"csv_ms_per_launch": a[2] / max(a[3], 1), "peer_wait_us_per_step": 1e3 * a[0] / max(a[1], 1)}
+                                 for a in all_wait] if world > 1 else None,
                     "whole_step_GBps": alg_bytes_step * args.steps / (ms * 1e-3) / 1e9,
                     "whole_step_frac": alg_bytes_step * args.steps / (ms * 1e-3) / 1e9 / peak,
                     "note": "value's step also holds an 805 MB device-to-device restore of the image and the device "

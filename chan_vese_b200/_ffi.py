@@ -25,7 +25,8 @@ class CsvParams(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("csv_step_launches", C.c_uint64), ("pm_step_launches", C.c_uint64),
-                ("csv_ms", C.c_double), ("pm_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("csv_ms", C.c_double), ("pm_ms", C.c_double), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("peer_wait_ms", C.c_double), ("peer_waits", C.c_uint64)]
 
 
 FRAME_FN = C.CFUNCTYPE(C.c_int, f64p, C.c_int, C.c_int, C.c_int, vp)

@@ -128,6 +128,8 @@ struct Job {
     CUtensorMap tm_u[2], tm_img;
 #endif
     unsigned int pm_seq = 0;
+    unsigned long long seen_wait_ns = 0;  // CommBox::wait_ns / wait_count already added to the context's stats
+    unsigned int seen_wait_count = 0;
     int pm_cur = -1;  // PM state buffer that holds the input of the last (quantising) step of the newest run; -1: none
 };
 static inline size_t esz(const Job *j) { return j->prec == CVB_PRECISION_F32 ? sizeof(float) : sizeof(double); }
@@ -754,9 +756,14 @@ static cvb_status check_peer_timeout(Job *j) {
     cvb_context *c = j->ctx;
     if (!j->p2p || !j->d_box) return CVB_OK;
     unsigned int flag = 0;
-    CU(c, cudaMemcpyAsync(&flag, reinterpret_cast<const char *>(j->d_box) + offsetof(CommBox, timed_out), sizeof flag,
-                          cudaMemcpyDeviceToHost, c->stream));
+    CommBox box;
+    CU(c, cudaMemcpyAsync(&box, j->d_box, sizeof box, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    flag = box.timed_out;
+    c->stats.peer_wait_ms += (double)(box.wait_ns - j->seen_wait_ns) * 1e-6;
+    c->stats.peer_waits += box.wait_count - j->seen_wait_count;
+    j->seen_wait_ns = box.wait_ns;
+    j->seen_wait_count = box.wait_count;
     if (flag)
         return fail(c, CVB_ERR_COMM, "rank %d timed out waiting for a neighbouring rank's boundary rows / region sums",
                     c->rank);

@@ -89,6 +89,9 @@ struct CommBox {
     unsigned int pm_ticket_up, pm_ticket_dn;  // boundary CTAs of the running PM launch that have finished
     unsigned int timed_out;          // sticky: a wait for a peer's flag gave up after SPIN_TIMEOUT_NS (the host reports
                                      // CVB_ERR_COMM instead of hanging; later waits return at once)
+    unsigned int wait_count;         // reductions this rank has waited for ...
+    unsigned long long wait_ns;      // ... and the time (globaltimer) its folding warp spent between raising its own flags
+                                     // and seeing the last peer's: what the slowest rank and the NVLink round trip cost
 };
 constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 struct CommView {

@@ -247,6 +247,7 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
         *reinterpret_cast<volatile unsigned int *>(&A.cv.box->produced) = prod;
     }
     __syncwarp();
+    const unsigned long long t_wait = global_ns();
     if (lane < A.cv.nranks) {
         st_release_sys(&A.cv.peer_box[lane]->arrive[A.cv.rank], prod);
         // ... and fold right here, in the tail of the same launch: wait until every rank has arrived (the other SMs of
@@ -256,7 +257,11 @@ __device__ __forceinline__ void finish_tile(const CsvArgs &A, int img, int seg, 
     }
     __syncwarp();  // lane p has acquired peer p's flag: with the warp barrier every lane may read every peer's sums
     csv_fold(A, 0, final_mode, prod);
-    if (lane == 0) A.cv.box->finalized = prod;
+    if (lane == 0) {
+        A.cv.box->finalized = prod;
+        A.cv.box->wait_ns += global_ns() - t_wait;
+        A.cv.box->wait_count += 1u;
+    }
 }
 
 }  // namespace cvb

@@ -67,6 +67,10 @@ typedef struct cvb_stats {
     double csv_ms;              /* device time of csv_step launches (CUDA events on the library's stream) */
     double pm_ms;               /* device time of pm_step launches */
     uint64_t h2d_bytes, d2h_bytes;
+    /* multi-GPU slab sessions: time the folding warp of the step kernels spent between publishing this rank's region sums
+     * and seeing the last peer's (the slowest rank + the NVLink round trip), and the number of reductions it covers */
+    double peer_wait_ms;
+    uint64_t peer_waits;
 } cvb_stats;
 
 typedef struct cvb_context cvb_context; /* one per GPU (and per rank) */
