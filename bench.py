@@ -16,8 +16,9 @@ combined over the ranks in row order) is identical for N = 1, 2, 4, 8.
 stop, images split evenly over the ranks, no communication; strong scaling over the fixed batch.
 
 `value`  : inputs resident in HBM when the timed region starts.
-`e2e`    : the same through the C ABI with HOST buffers -- every step uploads the uint8 planes from pinned memory
-           (later planes behind the diffusion of the earlier ones) and reads the bit-packed segmentation mask back.
+`e2e`    : the same through the C ABI with HOST buffers, as a stream of images through one session -- every step uploads
+           its uint8 planes from pinned memory (cvb_session_prefetch_image: the copy of step k+1's planes runs on a second
+           stream behind the solver of step k) and reads the bit-packed segmentation mask back.
 `extra`  : (N = 1, slabs) the other BASELINE configurations timed in the same run -- C1, C2 whole-job ms, C3 (4096^2
            gray, 2000 steps) with its own roofline fraction, the fp32 variant of C3 -- and `e2e_oneshot`: one call of
            cvb_segment (the seam INTEGRATION.md binds) with pageable host buffers, fp64 u in and out.
@@ -431,10 +432,14 @@ def run_slabs(args):
         return n_pm, n_csv
 
     def step_e2e():
-        # host buffers in, host buffer out: planes uploaded from pinned memory (later planes behind the diffusion of
-        # the earlier ones), the segmentation mask read back bit-packed
-        n_pm = sess.upload_image_smooth(views, PM["K"], PM["L"], PM["T"])
+        # host buffers in, host buffer out, every step: a stream of images through the session.  restore_image makes the
+        # image prefetched during the previous step current; the upload of the NEXT step's planes (pinned host memory ->
+        # HBM, on the copy stream) then runs behind this step's diffusion and level-set loop; the segmentation mask is read
+        # back bit-packed.  Every step uploads all of its input and downloads its result inside the timed region.
+        sess.restore_image()
+        sess.prefetch_image(views)
         sess.init_checkerboard()
+        n_pm = sess.perona_malik(PM["K"], PM["L"], PM["T"])
         n_csv, norm = sess.csv_run(prm, tol=0.0, max_steps=CSV_STEPS)
         sess.mask_packed(out=mask_view)
         last.update(n_pm=n_pm, n_csv=n_csv, norm=norm)
@@ -447,6 +452,7 @@ def run_slabs(args):
     digest_resident = (last["n_csv"], float(last["norm"]).hex())
     pix_iters = float(H) * W * (n_pm + n_csv) * args.steps
     value = pix_iters / (ms * 1e-3)
+    sess.prefetch_image(views)  # the first e2e step's image (the warm-up steps keep the pipeline primed)
     ms_e2e, _, st_e2e, _ = h.timed(step_e2e, args.steps, max(1, args.warmup // 3), False)
     e2e_value = pix_iters / (ms_e2e * 1e-3)
     # the end-to-end sequence must have produced the same mask (its buffer is the pinned one the timed steps filled)

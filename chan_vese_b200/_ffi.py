@@ -86,6 +86,7 @@ SIGNATURES = {
     "cvb_session_upload_image_smooth": (C.c_int, [vp, u8pp, C.c_double, C.c_double, C.c_double, intp]),
     "cvb_session_save_image": (C.c_int, [vp]),
     "cvb_session_restore_image": (C.c_int, [vp]),
+    "cvb_session_prefetch_image": (C.c_int, [vp, u8pp]),
     "cvb_session_release_scratch": (C.c_int, [vp]),
     "cvb_comm_create_id": (C.c_int, [vp, vp]),
     "cvb_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
@@ -105,6 +106,7 @@ SIGNATURES = {
     "cvb_batch_upload_images_smooth": (C.c_int, [vp, u8pp, C.c_double, C.c_double, C.c_double, intp]),
     "cvb_batch_save_images": (C.c_int, [vp]),
     "cvb_batch_restore_images": (C.c_int, [vp]),
+    "cvb_batch_prefetch_images": (C.c_int, [vp, u8pp]),
     "cvb_batch_release_scratch": (C.c_int, [vp]),
 }
 

@@ -128,6 +128,8 @@ struct Job {
     CUtensorMap tm_u[2], tm_img;
 #endif
     unsigned int pm_seq = 0;
+    cudaEvent_t ev_prefetched = nullptr, ev_restored = nullptr;  // prefetch_image / restore_image hand-over
+    bool prefetch_pending = false, prefetch_needs_halo = false;
     unsigned long long seen_wait_ns = 0;  // CommBox::wait_ns / wait_count already added to the context's stats
     unsigned int seen_wait_count = 0;
     int pm_cur = -1;  // PM state buffer that holds the input of the last (quantising) step of the newest run; -1: none
@@ -540,6 +542,9 @@ static void job_free(Job *j) {
     if (!j) return;
     cudaSetDevice(j->ctx->device);
     cudaStreamSynchronize(j->ctx->stream);
+    if (j->ctx->copy_stream) cudaStreamSynchronize(j->ctx->copy_stream);
+    if (j->ev_prefetched) cudaEventDestroy(j->ev_prefetched);
+    if (j->ev_restored) cudaEventDestroy(j->ev_restored);
     cudaFree(j->d_img);
     cudaFree(j->d_img_saved);
     cudaFree(j->d_u[0]);
@@ -793,6 +798,11 @@ static cvb_status job_upload_image(Job *j, const uint8_t *const *planes) {
 static cvb_status job_save_image(Job *j) {
     cvb_context *c = j->ctx;
     CU(c, cudaSetDevice(c->device));
+    if (j->prefetch_pending) {  // an unconsumed prefetch is overwritten: let it finish first
+        CU(c, cudaStreamWaitEvent(c->stream, j->ev_prefetched, 0));
+        j->prefetch_pending = false;
+    }
+    j->prefetch_needs_halo = false;
     const size_t bytes = (size_t)j->g.count * j->g.nch * j->g.plane_elems;
     if (!j->d_img_saved) CU(c, cudaMalloc(&j->d_img_saved, bytes));
     CU(c, cudaMemcpyAsync(j->d_img_saved, j->d_img, bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -803,7 +813,54 @@ static cvb_status job_restore_image(Job *j) {
     if (!j->d_img_saved) return fail(c, CVB_ERR_STATE, "no saved image (call save_image first)");
     CU(c, cudaSetDevice(c->device));
     const size_t bytes = (size_t)j->g.count * j->g.nch * j->g.plane_elems;
+    if (j->prefetch_pending) {  // the saved copy is being refilled by prefetch_image on the copy stream
+        CU(c, cudaStreamWaitEvent(c->stream, j->ev_prefetched, 0));
+        j->prefetch_pending = false;
+    }
     CU(c, cudaMemcpyAsync(j->d_img, j->d_img_saved, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (j->ev_restored) CU(c, cudaEventRecord(j->ev_restored, c->stream));
+    // a prefetched slab has no neighbour rows yet (a saved copy made by save_image has): exchange them now, collectively
+    if (j->prefetch_needs_halo) TRY(exchange_halo(j, j->d_img, 1, j->g.count * j->g.nch));
+    return CVB_OK;
+}
+// The NEXT image of a stream of images: copied from (pinned) host memory into the saved copy on the copy stream while the
+// solver works on the current one; restore_image then waits for the copy and makes it the current image.  Whole images
+// and batches; for row slabs the halo rows of the slab's first / last rows are filled by the caller's own neighbours'
+// uploads -- see the header.  Returns at once: the host buffers must stay untouched until the next restore_image.
+static cvb_status job_prefetch_image(Job *j, const uint8_t *const *planes) {
+    cvb_context *c = j->ctx;
+    if (!planes) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes is NULL");
+    CU(c, cudaSetDevice(c->device));
+    const Geom &g = j->g;
+    const size_t bytes = (size_t)g.count * g.nch * g.plane_elems;
+    if (!j->d_img_saved) {
+        CU(c, cudaMalloc(&j->d_img_saved, bytes));
+        CU(c, cudaMemsetAsync(j->d_img_saved, 0, bytes, c->stream));
+    }
+    if (!c->copy_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : c->copy_ev) CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (!j->ev_prefetched) {
+        CU(c, cudaEventCreateWithFlags(&j->ev_prefetched, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&j->ev_restored, cudaEventDisableTiming));
+        CU(c, cudaEventRecord(j->ev_restored, c->stream));
+    }
+    // the copy must not overtake a restore that still reads the saved copy (or the memset above)
+    CU(c, cudaEventRecord(j->ev_restored, c->stream));
+    CU(c, cudaStreamWaitEvent(c->copy_stream, j->ev_restored, 0));
+    const int rows = g.row_hi - g.row_lo;
+    for (int p = 0; p < g.count * g.nch; ++p) {
+        if (!planes[p]) return fail(c, CVB_ERR_INVALID_ARGUMENT, "planes[%d] is NULL", p);
+        CU(c, cudaMemcpy2DAsync(j->d_img_saved + (size_t)p * g.plane_elems + (size_t)HALO * g.pitch, g.pitch, planes[p], g.w, g.w,
+                                rows, cudaMemcpyHostToDevice, c->copy_stream));
+        c->stats.h2d_bytes += (uint64_t)rows * g.w;
+    }
+    CU(c, launch_replicate_halo(j->d_img_saved, (size_t)g.plane_elems, (size_t)g.pitch, g.count * g.nch, rows, g.row_lo == 0,
+                                g.row_hi == g.h, c->copy_stream));
+    CU(c, cudaEventRecord(j->ev_prefetched, c->copy_stream));
+    j->prefetch_pending = true;
+    j->prefetch_needs_halo = j->slab && c->nranks > 1;
     return CVB_OK;
 }
 static cvb_status job_download_image(Job *j, int first_plane, int nplanes, uint8_t *const *planes) {
@@ -1577,6 +1634,9 @@ extern "C" cvb_status cvb_session_upload_image_smooth(cvb_session *s, const uint
 }
 extern "C" cvb_status cvb_session_save_image(cvb_session *s) { return s ? job_save_image(s) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_session_restore_image(cvb_session *s) { return s ? job_restore_image(s) : CVB_ERR_INVALID_ARGUMENT; }
+extern "C" cvb_status cvb_session_prefetch_image(cvb_session *s, const uint8_t *const *planes) {
+    return s ? job_prefetch_image(s, planes) : CVB_ERR_INVALID_ARGUMENT;
+}
 extern "C" cvb_status cvb_session_release_scratch(cvb_session *s) {
     return s ? job_release_pm(s) : CVB_ERR_INVALID_ARGUMENT;
 }
@@ -1639,6 +1699,9 @@ extern "C" cvb_status cvb_batch_upload_images_smooth(cvb_batch *b, const uint8_t
 }
 extern "C" cvb_status cvb_batch_save_images(cvb_batch *b) { return b ? job_save_image(b) : CVB_ERR_INVALID_ARGUMENT; }
 extern "C" cvb_status cvb_batch_restore_images(cvb_batch *b) { return b ? job_restore_image(b) : CVB_ERR_INVALID_ARGUMENT; }
+extern "C" cvb_status cvb_batch_prefetch_images(cvb_batch *b, const uint8_t *const *planes) {
+    return b ? job_prefetch_image(b, planes) : CVB_ERR_INVALID_ARGUMENT;
+}
 extern "C" cvb_status cvb_batch_release_scratch(cvb_batch *b) {
     return b ? job_release_pm(b) : CVB_ERR_INVALID_ARGUMENT;
 }

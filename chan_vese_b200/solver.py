@@ -363,6 +363,12 @@ class Session:
     def restore_image(self):
         self.ctx.check(self._lib.cvb_session_restore_image(self._h))
 
+    def prefetch_image(self, channels):
+        """Start copying the NEXT image (keep `channels` alive and untouched until the next restore_image)."""
+        arrs, ptrs = _planes(channels, self.rows, self.w)
+        self._prefetch_keep = arrs
+        self.ctx.check(self._lib.cvb_session_prefetch_image(self._h, ptrs))
+
     def release_scratch(self):
         self.ctx.check(self._lib.cvb_session_release_scratch(self._h))
 
@@ -461,6 +467,17 @@ class Batch:
 
     def restore_images(self):
         self.ctx.check(self._lib.cvb_batch_restore_images(self._h))
+
+    def prefetch_images(self, images):
+        """Start copying the NEXT batch (keep `images` alive and untouched until the next restore_images)."""
+        arr = np.ascontiguousarray(images, dtype=np.uint8)
+        if arr.shape != (self.count, self.n, self.h, self.w):
+            raise ValueError("images shape %r, expected %r" % (arr.shape, (self.count, self.n, self.h, self.w)))
+        base = arr.ctypes.data
+        stride = self.h * self.w
+        ptrs = (_ffi.u8p * (self.count * self.n))(*[C.cast(base + p * stride, _ffi.u8p) for p in range(self.count * self.n)])
+        self._prefetch_keep = arr
+        self.ctx.check(self._lib.cvb_batch_prefetch_images(self._h, ptrs))
 
     def release_scratch(self):
         self.ctx.check(self._lib.cvb_batch_release_scratch(self._h))

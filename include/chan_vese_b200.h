@@ -210,6 +210,12 @@ cvb_status cvb_session_upload_image_smooth(cvb_session *s, const uint8_t *const 
  * save_image keeps a device copy of the current planes, restore_image brings it back (device to device). */
 cvb_status cvb_session_save_image(cvb_session *s);
 cvb_status cvb_session_restore_image(cvb_session *s);
+/* A stream of images through one session: prefetch_image copies the NEXT image from (pinned) host memory into the saved
+ * copy on a second stream and returns at once, while the solver works on the current image; the next restore_image waits
+ * for that copy (on the device, not on the host) and makes it current (row slabs: and exchanges the neighbour rows).
+ * The host planes must stay untouched until that restore_image has been called.  The upload of image k+1 is thereby
+ * hidden behind Perona-Malik + Chan-Vese of image k. */
+cvb_status cvb_session_prefetch_image(cvb_session *s, const uint8_t *const *planes);
 /* Frees the fp64 Perona-Malik scratch planes (they are re-allocated on demand).  Not for multi-GPU slab sessions:
  * their planes are mapped by the neighbouring ranks (CUDA IPC) for the session's lifetime -> CVB_ERR_STATE. */
 cvb_status cvb_session_release_scratch(cvb_session *s);
@@ -243,6 +249,7 @@ cvb_status cvb_batch_masks_packed(cvb_batch *b, int invert, uint8_t *bits);
 cvb_status cvb_batch_upload_images_smooth(cvb_batch *b, const uint8_t *const *planes, double K, double L, double T, int *steps);
 cvb_status cvb_batch_save_images(cvb_batch *b);
 cvb_status cvb_batch_restore_images(cvb_batch *b);
+cvb_status cvb_batch_prefetch_images(cvb_batch *b, const uint8_t *const *planes);
 cvb_status cvb_batch_release_scratch(cvb_batch *b);
 
 #ifdef __cplusplus

@@ -719,3 +719,32 @@ def test_results_do_not_depend_on_segments_per_cta(ctx):
             assert steps == out[0][1] and norm == out[0][2] and np.array_equal(u, out[0][0]), (tile, tol)
         ref, rs, _ = co.csv_run(img, u0, co.params(lambda1=[1.0, 0.7, 1.3]), tol, max_steps)
         assert rs == out[0][1] and rel_l2(out[0][0], ref) < TOL_U
+
+
+def test_prefetch_image_streams_images_through_a_session(ctx):
+    """prefetch_image / restore_image: image k+1 travels to the device while image k is being solved; every image gets
+    exactly the result of a plain upload."""
+    h, w = 120, 170
+    imgs = [synth.seastar(h, w, seed=s, arms=5 + s) for s in (41, 42, 43)]
+    prm = cv.make_params()
+
+    def solve(s):
+        s.init_checkerboard()
+        n = s.perona_malik(20.0, 0.25, 1.5)
+        steps, norm = s.csv_run(prm, tol=0.0, max_steps=9)
+        return s.download_image(), s.download_levelset(), n, steps, norm
+
+    ref = []
+    for im in imgs:
+        with cv.Session(ctx, 3, h, w) as s:
+            s.upload_image(im)
+            ref.append(solve(s))
+    with cv.Session(ctx, 3, h, w) as s:
+        s.prefetch_image(imgs[0])
+        for k in range(3):
+            s.restore_image()
+            if k + 1 < 3:
+                s.prefetch_image(imgs[k + 1])  # runs behind the solve below
+            got = solve(s)
+            assert got[2:] == ref[k][2:]
+            assert all(np.array_equal(a, b) for a, b in zip(got[0], ref[k][0])) and np.array_equal(got[1], ref[k][1])
