@@ -270,25 +270,27 @@ static int wave_aware_rows(int rows_per_rank, long long ctas_per_seg, int min_ta
     }
     return best;
 }
-// Modelled efficiency of tile length r for an image cut into nranks row slabs (cvb_slab_partition): the rank with the
-// most segments sets the pace; waves / ceil(waves) x priming overhead.  0 when the slabs have fewer than two waves.
-// (most < ...: the model is about whole waves of equal CTAs; 1.5 waves is the least it is trusted with)
+// Modelled efficiency of tile length r for an image cut into nranks row slabs (cvb_slab_partition): slabs are unions of
+// whole segments, the rank with the most rows sets the pace (every step ends in an all-rank reduction), and every CTA pays
+// a few rows' worth of priming.  0 when a slab would have fewer than 1.9 waves of CTAs.
+// Measured on B200 (profiles/README.md, r2g / r2k): at 16384^2 the csv_step time follows the rows per rank, NOT
+// ceil(waves) x tile length -- tiles of 40, 64 and 123 rows on 8 GPUs and 123 / 124 / 126 / 128 rows on one GPU are within
+// 1 % of each other -- so the model has no wave-quantisation term.
 static double slab_tile_eff(int h, int ncb, int r, int nranks) {
     const int nseg = ceil_div(h, r);
-    int most = 0;
+    int most_rows = 0, most_segs = 0;
     for (int k = 0; k < nranks; ++k) {
         const int s0 = group_seg_begin(k * (NGROUPS / nranks), nseg), s1 = group_seg_begin((k + 1) * (NGROUPS / nranks), nseg);
-        most = std::max(most, s1 - s0);
+        most_rows = std::max(most_rows, std::min(s1 * r, h) - std::min(s0 * r, h));
+        most_segs = std::max(most_segs, s1 - s0);
     }
-    const double waves = (double)most * ncb / kSlots;
-    if (waves < 1.5) return 0.0;
-    const double ideal = (double)h / nranks * ncb / kSlots;  // in rows per slot
-    return ideal / (ceil(waves) * (r + 3.5));
+    if ((double)most_segs * ncb / kSlots < 1.9 || most_rows <= 0) return 0.0;  // (nothing below 1.9 waves has been measured)
+    return ((double)h / nranks) / most_rows * (r / (r + 3.5));
 }
 // Rows per tile of a single image.  The tiling fixes the order of the fused sums (reduce.cuh), so it must NOT depend on
 // the number of GPUs the image is spread over: a run on 1, 2, 4 or 8 GPUs then gives bit-identical results with the
 // automatic choice too.  The choice maximises the single-GPU efficiency plus the worst efficiency among the slab
-// decompositions (2, 4, 8 ranks) that are large enough to be worth running (>= 2 waves per rank).
+// decompositions (2, 4, 8 ranks) that are large enough to be worth running.
 static int auto_seg_rows(int h, int w, int count, int /*nranks: deliberately unused*/) {
     const int ncb = ceil_div(w, CSV_CB);
     if (count == 1) {
@@ -298,11 +300,14 @@ static int auto_seg_rows(int h, int w, int count, int /*nranks: deliberately unu
             const double e1 = slab_tile_eff(h, ncb, r, 1);
             if (e1 <= 0.0) continue;
             double worst = e1;
+            bool ok = true;
             for (int n : {2, 4, 8}) {
                 if ((double)h / n * ncb / 48.0 < 2.0 * kSlots) continue;  // not worth a slab run at any tile length
                 const double e = slab_tile_eff(h, ncb, r, n);
+                if (e <= 0.0) ok = false;
                 worst = std::min(worst, e);
             }
+            if (!ok) continue;
             const double score = e1 + worst;
             if (score > best_score + 1e-9) {
                 best_score = score;
