@@ -1006,13 +1006,15 @@ static cvb_status job_init_checkerboard(Job *j) {
     cvb_context *c = j->ctx;
     CU(c, cudaSetDevice(c->device));
     const Geom &g = j->g;
-    std::vector<signed char> s((size_t)g.h + g.w);
-    // sign(si*sj) = sign(si)*sign(sj) unless the product underflows to zero: |sin| >= ~1e-16 or exactly 0 here
-    for (int i = 0; i < g.h; ++i) s[i] = sign_of(sin(kPi * i / 5));
-    for (int jx = 0; jx < g.w; ++jx) s[(size_t)g.h + jx] = sign_of(sin(kPi * jx / 5));
-    if (!j->d_sign) CU(c, cudaMalloc(&j->d_sign, s.size()));
-    CU(c, cudaMemcpyAsync(j->d_sign, s.data(), s.size(), cudaMemcpyHostToDevice, c->stream));
-    c->stats.h2d_bytes += s.size();
+    if (!j->d_sign) {  // the sign vectors depend on h and w only: computed and uploaded once per job
+        std::vector<signed char> s((size_t)g.h + g.w);
+        // sign(si*sj) = sign(si)*sign(sj) unless the product underflows to zero: |sin| >= ~1e-16 or exactly 0 here
+        for (int i = 0; i < g.h; ++i) s[i] = sign_of(sin(kPi * i / 5));
+        for (int jx = 0; jx < g.w; ++jx) s[(size_t)g.h + jx] = sign_of(sin(kPi * jx / 5));
+        CU(c, cudaMalloc(&j->d_sign, s.size()));
+        CU(c, cudaMemcpy(j->d_sign, s.data(), s.size(), cudaMemcpyHostToDevice));
+        c->stats.h2d_bytes += s.size();
+    }
     for (int m = 0; m < g.count; ++m) {
         if (is_f32(j))
             CU(c, launch_checkerboard_f32(reinterpret_cast<float *>(u_plane(j, 0, m)), j->d_sign, j->d_sign + g.h, g.row_lo,
@@ -1025,8 +1027,7 @@ static cvb_status job_init_checkerboard(Job *j) {
     CU(c, launch_replicate_halo(j->d_u[0], (size_t)g.plane_elems * esz(j), (size_t)g.pitch * esz(j), g.count,
                                 g.row_hi - g.row_lo, g.row_lo == 0, g.row_hi == g.h, c->stream));
     CU(c, cudaMemsetAsync(j->d_state, 0, (size_t)g.count * sizeof(CsvState), c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));  // s goes out of scope
-    return CVB_OK;
+    return CVB_OK;  // asynchronous: everything that follows is ordered on the stream
 }
 
 // perona_malik, src/main.cpp:478-560, on the resident image planes (in place)

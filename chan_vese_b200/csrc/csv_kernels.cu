@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CSV_MIN_CTAS) csv_step_kernel(con
 // Sums of the CURRENT level set and of the image: sum a, sum I_k*a, sum I_k, sum mean_k(I)^2.
 // Gives the first step's c1/c2 (src/main.cpp:973-974) and the stop condition (:949-960).
 template <int NCH>
-__global__ void __launch_bounds__(CTA_THREADS, 8) csv_init_kernel(const __grid_constant__ CsvArgs A, int final_mode) {
+__global__ void __launch_bounds__(CTA_THREADS, 16) csv_init_kernel(const __grid_constant__ CsvArgs A, int final_mode) {
     const Geom &G = A.g;
     __shared__ double s_tab[ATAN_TAB_N];
     const int lane = threadIdx.x;
@@ -909,31 +909,47 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) csv_init_kernel(const __grid_c
     for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
     if (lane >= 1 && a < w) {
         const bool v1 = a + 1 < w;
-        for (int i = ra; i < rb; ++i) {
-            const size_t off = (size_t)(i - G.row_lo + HALO) * G.pitch + a;
-            const double2 U = __ldg(reinterpret_cast<const double2 *>(uin + off));
-            double a0 = atan_over_pi(U.x * inv_eps, s_tab);
-            double a1 = atan_over_pi(U.y * inv_eps, s_tab);
-            a1 = v1 ? a1 : 0.0;
-            acc[ACC_A] += a0;
-            acc[ACC_A] += a1;
-            double m0 = 0.0, m1 = 0.0;
+        constexpr int RB = 4;  // rows per batch: all loads of a batch are issued before its arithmetic (the pass is pure
+                               // streaming; one dependent load per row left it latency-bound at a third of the HBM rate)
+        for (int i0 = ra; i0 < rb; i0 += RB) {
+            double2 Ub[RB];
+            unsigned int Bb[RB][NCH];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const unsigned int b = __ldg(reinterpret_cast<const unsigned short *>(im + (size_t)c * G.plane_elems + off));
-                const double I0 = u8_to_double(b & 0xffu);
-                const double I1 = v1 ? u8_to_double(b >> 8) : 0.0;
-                acc[ACC_IA + c] = fma(I0, a0, acc[ACC_IA + c]);
-                acc[ACC_IA + c] = fma(I1, a1, acc[ACC_IA + c]);
-                acc[ACC_I + c] += I0;
-                acc[ACC_I + c] += I1;
-                m0 += I0;
-                m1 += I1;
+            for (int k = 0; k < RB; ++k) {
+                const int i = min(i0 + k, rb - 1);  // rows past the segment re-read its last row and are not summed
+                const size_t off = (size_t)(i - G.row_lo + HALO) * G.pitch + a;
+                Ub[k] = __ldg(reinterpret_cast<const double2 *>(uin + off));
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+                    Bb[k][c] = __ldg(reinterpret_cast<const unsigned short *>(im + (size_t)c * G.plane_elems + off));
             }
-            m0 *= inv_n;
-            m1 *= inv_n;
-            acc[ACC_SQ] = fma(m0, m0, acc[ACC_SQ]);
-            acc[ACC_SQ] = fma(m1, m1, acc[ACC_SQ]);
+#pragma unroll
+            for (int k = 0; k < RB; ++k) {
+                if (i0 + k >= rb) break;
+                const double2 U = Ub[k];
+                double a0 = atan_over_pi(U.x * inv_eps, s_tab);
+                double a1 = atan_over_pi(U.y * inv_eps, s_tab);
+                a1 = v1 ? a1 : 0.0;
+                acc[ACC_A] += a0;
+                acc[ACC_A] += a1;
+                double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const unsigned int b = Bb[k][c];
+                    const double I0 = u8_to_double(b & 0xffu);
+                    const double I1 = v1 ? u8_to_double(b >> 8) : 0.0;
+                    acc[ACC_IA + c] = fma(I0, a0, acc[ACC_IA + c]);
+                    acc[ACC_IA + c] = fma(I1, a1, acc[ACC_IA + c]);
+                    acc[ACC_I + c] += I0;
+                    acc[ACC_I + c] += I1;
+                    m0 += I0;
+                    m1 += I1;
+                }
+                m0 *= inv_n;
+                m1 *= inv_n;
+                acc[ACC_SQ] = fma(m0, m0, acc[ACC_SQ]);
+                acc[ACC_SQ] = fma(m1, m1, acc[ACC_SQ]);
+            }
         }
     }
     finish_tile<NCH, true>(A, img, seg, cb, G.ncb_csv, acc, final_mode);

@@ -171,6 +171,11 @@ def test_config2(ctx, golden_c2):
     assert abs(np.linalg.norm(u) - float(golden_c2["u_norm"])) <= TOL_U * float(golden_c2["u_norm"])
     ref_mask = np.unpackbits(golden_c2["mask"])[:c["h"] * c["w"]].reshape(c["h"], c["w"])
     assert (ctx.mask(u) == ref_mask).mean() >= 0.999
+    # the whole level set (the fixture keeps every 4th sample only): the C oracle on the same planes, all 132 steps
+    ref, rs, rn = co.csv_run(list(golden_c2["pm"]), co.levelset_checkerboard(c["h"], c["w"]),
+                             co.params(nu=k["nu"], dt=k["dt"], lambda1=k["lambda1"]), k["tol"], k["max_steps"])
+    assert rs == steps and rel_l2(u, ref) < TOL_U and abs(nrm - rn) <= 1e-6 * rn
+    assert np.array_equal(ctx.mask(u), co.mask(ref))
 
 
 def test_config3_reduced_ring_init(ctx):
@@ -182,6 +187,20 @@ def test_config3_reduced_ring_init(ctx):
     ref, rs, _ = co.csv_run(img, u0, co.params(), 0.0, 40)
     assert steps == rs == 40
     assert rel_l2(u, ref) < TOL_U
+    assert (ctx.mask(u) == co.mask(ref)).mean() >= 0.999
+
+
+def test_config3_all_2000_steps_reduced_size(ctx):
+    """C3's step count -- 2000 iterations, tolerance 0, grayscale, ring init -- at 256^2 (the oracle needs ~10 s): the
+    level set stays within the tolerance over the whole run, not just over its first steps."""
+    n = 256
+    img = synth.two_phase(n, n, seed=3, discs=6)
+    u0 = cv.levelset_circ(n, n, n // 2, n // 2, n // 4)
+    u, steps, nrm = ctx.csv_run(img, u0, cv.make_params(nch=1), tol=0.0, max_steps=2000)
+    ref, rs, rn = co.csv_run(img, u0, co.params(), 0.0, 2000)
+    assert steps == rs == 2000
+    assert rel_l2(u, ref) < TOL_U
+    assert abs(nrm - rn) <= 1e-6 * max(rn, 1e-300)
     assert (ctx.mask(u) == co.mask(ref)).mean() >= 0.999
 
 
