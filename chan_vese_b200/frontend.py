@@ -185,6 +185,10 @@ def _validate(o):
         raise MsgExit("Cannot have negative or zero timestep: %f." % o.dt)
     if o.mu < 0:
         raise MsgExit("Length penalty parameter cannot be negative: %f." % o.mu)
+    if o.epsilon <= 0:
+        # deliberate deviation: the reference's own check (src/main.cpp:831-834) tests an option name that does not exist
+        # and never fires; epsilon = 0 divides by zero in the regularised delta.  Same message as bin/chan_vese (cli/).
+        raise MsgExit("Cannot have negative or zero smoothing parameter: %f." % o.epsilon)
     n = 1 if o.grayscale else 3
     for name in ("lambda1", "lambda2"):
         lam = getattr(o, name)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call A: tests, bench, tile sweep, I256 variant A/B, C3 tile sweep, ncu launch list + full capture
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $O/r2a_smi.txt
 ( time python -m pytest tests -m gpu -x -q ) > $O/r2a_tests.log 2>&1; echo "tests rc=$?" >> $O/r2a_tests.log

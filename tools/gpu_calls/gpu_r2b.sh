@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call B: PM temporal blocking (tests, bench, ncu), register-budget variants of csv_step
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 ( time python -m pytest tests -m gpu -x -q ) > $O/r2b_tests.log 2>&1; echo "tests rc=$?" >> $O/r2b_tests.log
 tail -6 $O/r2b_tests.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call C (2 GPUs): tests, slab bit-identity soak, N=1 and N=2 bench with PDL + overlapped upload on
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 ( time python -m pytest tests -m gpu -x -q ) > $O/r2c_tests.log 2>&1; echo "tests rc=$?" >> $O/r2c_tests.log
 tail -4 $O/r2c_tests.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call D (1 GPU): full gpu test suite, bench with extras, batch workload
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 ( time python -m pytest tests -m gpu -q ) > $O/r2d_tests.log 2>&1; echo "tests rc=$?" >> $O/r2d_tests.log
 tail -4 $O/r2d_tests.log

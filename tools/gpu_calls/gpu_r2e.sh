@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 ( time python -m pytest tests -m gpu -q ) > $O/r2e_tests.log 2>&1; echo "tests rc=$?" >> $O/r2e_tests.log
 tail -4 $O/r2e_tests.log

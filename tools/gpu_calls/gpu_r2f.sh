@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call F (8 GPUs): slab bit-identity at 8 ranks, bench at 8 / 4 ranks (PDL + overlapped upload on), batch workload
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 timeout 300 $TR --nproc-per-node 8 --master-port 29511 tools/multigpu_check.py --size 4096 --csv-steps 12 --repeat 3 --trace > $O/r2f_mg8.log 2> $O/r2f_mg8.err; echo "mg8 rc=$?"; tail -1 $O/r2f_mg8.log

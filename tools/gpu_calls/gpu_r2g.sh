@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call G (8 GPUs): tile-length sweep of csv_step and pm2 at 8 ranks (how much of the per-launch loss is tail?)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "segments_per_cta or config1 or config2 or early_stop" > $O/r2g_tests.log 2>&1; echo "tests rc=$?"; tail -2 $O/r2g_tests.log
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 8"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call H (1 GPU): full tests; the TMA build variant: parity tests, bench, ncu of both row loops
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 ( time python -m pytest tests -m gpu -q ) > $O/r2h_tests.log 2>&1; echo "tests rc=$?" >> $O/r2h_tests.log; tail -3 $O/r2h_tests.log
 V=chan_vese_b200/lib/variants/libcvb_tma.so

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call I (2 GPUs): slab bit-identity with the new step tail, bench at 2 ranks
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 timeout 300 $TR --master-port 29511 tools/multigpu_check.py --size 4096 --csv-steps 12 --repeat 3 > $O/r2i_mg2.log 2> $O/r2i_mg2.err; echo "mg2 rc=$?"; tail -1 $O/r2i_mg2.log

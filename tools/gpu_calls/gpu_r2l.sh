@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call L (1 GPU): full tests, bench with extras, ncu launch list + full capture of csv_step (profiles/r2_*)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 ( time python -m pytest tests -m gpu -q ) > $O/r2l_tests.log 2>&1; echo "tests rc=$?" >> $O/r2l_tests.log; tail -3 $O/r2l_tests.log
 python bench.py --steps 5 --warmup 3 > $O/r2l_bench.json 2> $O/r2l_bench.err; echo "bench rc=$?"
