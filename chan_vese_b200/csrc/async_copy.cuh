@@ -8,6 +8,10 @@ namespace cvb {
 __device__ __forceinline__ void cp_async16(unsigned int dst_shared, const void *src_global) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src_global) : "memory");
 }
+// 8-byte chunks (fp32 rows: two columns per lane); .cg exists for 16 bytes only, 8 bytes go through L1 (.ca)
+__device__ __forceinline__ void cp_async8(unsigned int dst_shared, const void *src_global) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_shared), "l"(src_global) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's committed groups are still in flight
 template <int N>

@@ -5,6 +5,7 @@
 // Same mapping as the fp64 kernels (one warp per CTA, 64-column strips, two columns per lane, halo lanes, row
 // recurrences in registers, flux form for PM); algorithmic traffic 8+N B per pixel-iteration (CSV) and 8 B per
 // channel-pixel-iteration (PM).
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "kernels.h"
 #include "math.cuh"
@@ -187,6 +188,187 @@ __device__ __forceinline__ void csv_rows_f32(const float *__restrict__ uin, floa
     for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = dI[c] + (double)accI[c];
 }
 
+// ---- the same row loop fed by a cp.async shared-memory ring (as csv_rows_ring of the fp64 kernel) ------------------
+// The register-prefetch loop above is latency-bound for the reason the fp64 kernels were before their rings: within 128
+// registers ptxas sinks the prefetch loads next to their first use.  Rows travel HBM -> shared memory RINGF_NS - 1 rows
+// ahead; the east / west neighbours of a row are read from the ring instead of being shuffled.
+// Slot of row k (RINGF_SLOT bytes at (k % RINGF_NS) * RINGF_SLOT):
+//   [8 + 8*j, +8)           chunk j = 0..32 of the u row: columns cs-2+2j, cs-1+2j (fp32); chunk 32 = lane 31's east neighbour
+//   [RINGF_IMG + 80*c, +80) image row of channel c from the 16-byte aligned column (cs-2) & ~15
+constexpr int RINGF_NS = 8;
+constexpr int RINGF_U = 8;
+constexpr int RINGF_IMG = 288;
+constexpr int RINGF_SLOT = 544;
+constexpr int RINGF_BYTES = RINGF_NS * RINGF_SLOT;
+static_assert(RINGF_U + 33 * 8 <= RINGF_IMG && RINGF_IMG + 80 * MAX_CH <= RINGF_SLOT, "fp32 ring slot layout");
+static_assert(RINGF_NS - 1 <= TAIL_ROWS, "tail padding too small for the fp32 ring");
+
+template <int NCH, bool EDGE>
+__device__ __forceinline__ void csv_rows_ring_f32(const float *__restrict__ uin, float *__restrict__ uout,
+                                                  const uint8_t *__restrict__ im, const Geom &G, const float (&cA)[NCH],
+                                                  const float (&cB)[NCH], float q0c, float alphap, float eps2, float inv_eps,
+                                                  unsigned char *ring, int ra, int rb, int cs, int lane, double (&acc)[NACC]) {
+    const int w = G.w;
+    const int a = cs - 2 + 2 * lane;
+    const size_t pitch = (size_t)G.pitch, pe = (size_t)G.plane_elems;
+    const bool first = EDGE && a == 0, last0 = EDGE && a == w - 1, last1 = EDGE && a + 1 == w - 1;
+    const bool v0 = lane >= 1 && (!EDGE || a < w), v1 = lane >= 1 && (!EDGE || a + 1 < w);
+    const bool ok1 = !EDGE || (a >= 0 && a < G.pitch);
+    // copies of one row: every lane its own 8-byte chunk of u; lanes 0 .. 5*NCH-1 a 16-byte chunk of the image strips;
+    // lane 15 the 33rd u chunk
+    const int s_al = (cs - 2) & ~15, dsh = (cs - 2) - s_al;
+    const float *src1 = uin + (size_t)(ra - G.row_lo + HALO) * pitch + a;  // row ra, advanced by pitch per issued row
+    const uint8_t *src2 = nullptr;
+    unsigned int dst2 = 0;
+    bool ok2 = false;
+    if (lane < 5 * NCH) {
+        const int c = lane / 5, q = lane % 5, col = s_al + 16 * q;
+        src2 = im + (size_t)c * pe + (size_t)(ra - G.row_lo + HALO) * pitch + col;
+        dst2 = RINGF_IMG + 80 * c + 16 * q;
+        ok2 = !EDGE || (col >= 0 && col < G.pitch);
+    }
+    const bool ok3 = lane == 15 && (!EDGE || cs - 2 + 64 < G.pitch);
+    const float *src3 = uin + (size_t)(ra - G.row_lo + HALO) * pitch + (cs - 2 + 64);
+    const unsigned int ring_s = (unsigned int)__cvta_generic_to_shared(ring);
+    auto issue = [&](unsigned int slot_off) {
+        if (ok1) cp_async8(ring_s + slot_off + RINGF_U + 8 * lane, src1);
+        if (ok2) cp_async16(ring_s + slot_off + dst2, src2);
+        if (ok3) cp_async8(ring_s + slot_off + RINGF_U + 8 * 32, src3);
+        cp_async_commit();
+        src1 += pitch;
+        src2 += pitch;
+        src3 += pitch;
+    };
+#pragma unroll
+    for (int k = 0; k < RINGF_NS - 1; ++k) issue(k * RINGF_SLOT);
+    // rows ra-2, ra-1 (own columns only) straight from global memory
+    const float *pr = uin + (size_t)(ra - 2 - G.row_lo + HALO) * pitch + a;
+    const float2 R0 = ldf2(pr, ok1), R1 = ldf2(pr + pitch, ok1);
+    const unsigned char *my8 = ring + RINGF_U + 8 * lane;  // + slot: own chunk; west neighbour at -4, east at +8
+    const unsigned char *my2 = ring + RINGF_IMG + dsh + 2 * lane;  // + slot + 80 c: own two image bytes
+    cp_async_wait<RINGF_NS - 3>();  // rows ra and ra+1 have landed
+    __syncwarp();
+    float2 C = *reinterpret_cast<const float2 *>(my8);
+    float CW = *reinterpret_cast<const float *>(my8 - 4);
+    float CE = *reinterpret_cast<const float *>(my8 + 8);
+    float dN0 = C.x - R1.x, dN1 = C.y - R1.y;
+    float nyp0 = normal_f32(dN0, dN0 + (R1.x - R0.x)), nyp1 = normal_f32(dN1, dN1 + (R1.y - R0.y));
+    if (ra == 0) {  // image top: ny(-1) := ny(0) (src/main.cpp:372)
+        const float2 q = *reinterpret_cast<const float2 *>(my8 + RINGF_SLOT);
+        nyp0 = normal_f32(q.x - C.x, (q.x - C.x) + dN0);
+        nyp1 = normal_f32(q.y - C.y, (q.y - C.y) + dN1);
+    }
+    float accA = 0.0f, accS = 0.0f, accI[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) accI[c] = 0.0f;
+    double dA = 0.0, dS = 0.0, dI[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) dI[c] = 0.0;
+    float *po = uout + (size_t)(ra - G.row_lo + HALO) * pitch + a;
+    const int n = rb - ra;
+
+    // one row: s_wr = slot of row i-1 (free, receives row i+NS-1), s_img = slot of row i, s_u = slot of row i+1
+    auto row = [&](unsigned int s_wr, unsigned int s_img, unsigned int s_u) {
+        issue(s_wr);
+        cp_async_wait<RINGF_NS - 2>();  // row i+1 has landed
+        __syncwarp();
+        const float2 S = *reinterpret_cast<const float2 *>(my8 + s_u);
+        const float SW = *reinterpret_cast<const float *>(my8 + s_u - 4);
+        const float SE = *reinterpret_cast<const float *>(my8 + s_u + 8);
+        unsigned int Ib[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) Ib[c] = *reinterpret_cast<const unsigned short *>(my2 + s_img + 80 * c);
+        // curvature (:342-375)
+        const float upy0 = S.x - C.x, upy1 = S.y - C.y;
+        const float ny0 = normal_f32(upy0, upy0 + dN0), ny1 = normal_f32(upy1, upy1 + dN1);
+        float Wn = CW, E2 = CE, E0 = C.y;
+        if (EDGE) {
+            Wn = first ? C.x : Wn;
+            E0 = last0 ? C.x : C.y;
+            E2 = last1 ? C.y : E2;
+        }
+        const float nx0 = normal_f32(E0 - C.x, E0 - Wn), nx1 = normal_f32(E2 - C.y, E2 - C.x);
+        const float nxw = __shfl_up_sync(0xffffffffu, nx1, 1);
+        float kx0 = nx0 - nxw;
+        if (EDGE) kx0 = first ? 0.0f : kx0;
+        const float kap0 = kx0 + (ny0 - nyp0), kap1 = (nx1 - nx0) + (ny1 - nyp1);
+        // data term + combine (:968-985), delta (:988-992), update (:994)
+        float I0[NCH], I1[NCH], t0 = q0c, t1 = q0c;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            I0[c] = u8_to_float(Ib[c] & 0xffu);
+            I1[c] = u8_to_float(Ib[c] >> 8);
+            t0 = fmaf(fmaf(cA[c], I0[c], cB[c]), I0[c], t0);
+            t1 = fmaf(fmaf(cA[c], I1[c], cB[c]), I1[c], t1);
+        }
+        t0 = fmaf(kap0, alphap, t0);
+        t1 = fmaf(kap1, alphap, t1);
+        const float du0 = t0 * rcp_f32(fmaf(C.x, C.x, eps2)), du1 = t1 * rcp_f32(fmaf(C.y, C.y, eps2));
+        const float un0 = C.x + du0, un1 = C.y + du1;
+        if (EDGE) {
+            if (v1)
+                *reinterpret_cast<float2 *>(po) = make_float2(un0, un1);
+            else if (v0)
+                *po = un0;
+        } else if (lane) {
+            *reinterpret_cast<float2 *>(po) = make_float2(un0, un1);
+        }
+        po += pitch;
+        // sums of the updated level set and of du^2
+        float a0 = atan_over_pi_f32(un0 * inv_eps), a1 = atan_over_pi_f32(un1 * inv_eps);
+        float dq0 = du0, dq1 = du1;
+        if (EDGE) {
+            a0 = v0 ? a0 : 0.0f;
+            a1 = v1 ? a1 : 0.0f;
+            dq0 = v0 ? dq0 : 0.0f;
+            dq1 = v1 ? dq1 : 0.0f;
+        }
+        accA += a0 + a1;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) accI[c] = fmaf(I1[c], a1, fmaf(I0[c], a0, accI[c]));
+        accS = fmaf(dq1, dq1, fmaf(dq0, dq0, accS));
+        dN0 = upy0;
+        dN1 = upy1;
+        nyp0 = ny0;
+        nyp1 = ny1;
+        C = S;
+        CW = SW;
+        CE = SE;
+    };
+    auto fold = [&]() {  // keep the fp32 running sums short: into fp64 every 16 rows
+        dA += (double)accA;
+        dS += (double)accS;
+        accA = accS = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            dI[c] += (double)accI[c];
+            accI[c] = 0.0f;
+        }
+    };
+    int r = 0;
+    unsigned int tog = 0;  // offset of slot 0 or slot 4: the slot of the first row of a group of four
+#pragma unroll 1
+    for (; r + 4 <= n; r += 4) {
+        const unsigned int t2 = tog ^ (4 * RINGF_SLOT);
+        row(t2 + 3 * RINGF_SLOT, tog, tog + RINGF_SLOT);
+        row(tog, tog + RINGF_SLOT, tog + 2 * RINGF_SLOT);
+        row(tog + RINGF_SLOT, tog + 2 * RINGF_SLOT, tog + 3 * RINGF_SLOT);
+        row(tog + 2 * RINGF_SLOT, tog + 3 * RINGF_SLOT, t2);
+        tog = t2;
+        if ((r & 12) == 12) fold();
+    }
+#pragma unroll 1
+    for (; r < n; ++r) {
+        const unsigned int k = (unsigned int)r;
+        row(((k + RINGF_NS - 1) % RINGF_NS) * RINGF_SLOT, (k % RINGF_NS) * RINGF_SLOT, ((k + 1) % RINGF_NS) * RINGF_SLOT);
+    }
+    cp_async_wait<0>();  // nothing may land in the ring after the CTA has gone
+    acc[ACC_A] = dA + (double)accA;
+    acc[ACC_SQ] = dS + (double)accS;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[ACC_IA + c] = dI[c] + (double)accI[c];
+}
+
 __device__ __noinline__ void replicate_border_rows_f32(float *uout, const Geom &G, int ra, int rb, int a) {
     if (ra == 0) {
         const float2 v = __ldcg(reinterpret_cast<const float2 *>(uout + (size_t)(0 - G.row_lo + HALO) * G.pitch + a));
@@ -234,12 +416,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 16) csv_step_f32_kernel(const __g
 #pragma unroll
     for (int v = 0; v < NACC; ++v) acc[v] = 0.0;
     const bool interior = cb > 0 && (cb + 1) * CSV_CB < G.w;
+    __shared__ __align__(16) unsigned char s_ring[RINGF_BYTES];
+#ifdef CVB_F32_NO_RING  // the register-prefetch loop of round 1 (comparison builds)
     if (interior)
         csv_rows_f32<NCH, false>(uin, uout, im, G, cA, cB, (float)q0, (float)(A.alpha * kd), (float)(A.eps * A.eps),
                                  (float)A.inv_eps, ra, rb, a, lane, acc);
     else
         csv_rows_f32<NCH, true>(uin, uout, im, G, cA, cB, (float)q0, (float)(A.alpha * kd), (float)(A.eps * A.eps),
                                 (float)A.inv_eps, ra, rb, a, lane, acc);
+#else
+    if (interior)
+        csv_rows_ring_f32<NCH, false>(uin, uout, im, G, cA, cB, (float)q0, (float)(A.alpha * kd), (float)(A.eps * A.eps),
+                                      (float)A.inv_eps, s_ring, ra, rb, cs, lane, acc);
+    else
+        csv_rows_ring_f32<NCH, true>(uin, uout, im, G, cA, cB, (float)q0, (float)(A.alpha * kd), (float)(A.eps * A.eps),
+                                     (float)A.inv_eps, s_ring, ra, rb, cs, lane, acc);
+#endif
     if (lane == 0) {
 #pragma unroll
         for (int v = 0; v < NACC; ++v) acc[v] = 0.0;  // halo lane
