@@ -98,3 +98,23 @@ def test_synthetic_inputs_are_deterministic():
     part = synth.hashed_scene_rows(512, 384, 200, 330, cell=128)
     assert all(np.array_equal(w[200:330], p) for w, p in zip(whole, part))  # slabs agree with the whole image
     assert np.array_equal(synth.batch_images(3, 2, 64, 64)[1], np.stack(synth.batch_image(4, 64, 64)))
+
+
+def test_tile_choice_does_not_depend_on_the_rank_count_and_balances_the_slabs():
+    """The tiling fixes the order of the fused sums, so the automatic tile length must be the same for every GPU count
+    (bit-identical results at 1, 2, 4, 8 GPUs); it is chosen so that the slabs of 2, 4 and 8 ranks are balanced."""
+    for h, w in [(16384, 16384), (8192, 8192), (12000, 9000), (4096, 4096), (430, 640)]:
+        t = cv.auto_tile_rows(h, w, 1, 1)
+        assert all(cv.auto_tile_rows(h, w, 1, n) == t for n in (2, 4, 8, 16))
+    h = w = 16384
+    t = cv.auto_tile_rows(h, w)
+    for n in (2, 4, 8):
+        rows = [hi - lo for lo, hi in (cv.slab_partition(h, t, n, r) for r in range(n))]
+        assert sum(rows) == h and max(rows) <= 1.01 * h / n, (n, rows)
+
+
+def test_release_scratch_and_trim_are_declared_and_epsilon_is_validated():
+    from chan_vese_b200 import frontend as fe
+    with pytest.raises(fe.MsgExit) as e:
+        fe._validate(fe._parser().parse_args(["-i", __file__, "-e", "0"]))
+    assert "smoothing parameter" in str(e.value)
