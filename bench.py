@@ -20,7 +20,8 @@ stop, images split evenly over the ranks, no communication; strong scaling over 
            its uint8 planes from pinned memory (cvb_session_prefetch_image: the copy of step k+1's planes runs on a second
            stream behind the solver of step k) and reads the bit-packed segmentation mask back.
 `extra`  : (N = 1, slabs) the other BASELINE configurations timed in the same run -- C1, C2 whole-job ms, C3 (4096^2
-           gray, 2000 steps) with its own roofline fraction, the fp32 variant of C3 -- and `e2e_oneshot`: one call of
+           gray, 2000 steps) with its own roofline fraction, the fp32 variant of C3, 512 of C5's images as one batch --
+           and `e2e_oneshot`: one call of
            cvb_segment (the seam INTEGRATION.md binds) with pageable host buffers, fp64 u in and out.
 `--impl reference`: the reference's CPU path (pass-structured OpenMP port oracle/ref_cpu.cpp; the reference itself
            needs OpenCV 2.4 + Boost and cannot be built here) on a bounded sample of the same workload.
@@ -364,6 +365,52 @@ def time_config(h, name, fp32=False, reps=3):
     return res
 
 
+def time_batch_sample(h, count=512):
+    """configs[4] on this GPU alone: `count` of the 4096 images (what one rank of an 8-GPU run holds), one batch job."""
+    import numpy as np
+    cv, torch = h.cv, h.torch
+    from chan_vese_b200 import synth
+    c = synth.CONFIGS["C5"]
+    hh, ww, n = c["h"], c["w"], c["n"]
+    k = dict(c["csv"])
+    max_steps = k.pop("max_steps")
+    tol = k.pop("tol", 1e-3)
+    prm = cv.make_params(nch=n, **k)
+    base = synth.batch_images(0, 64, hh, ww)
+    imgs = np.ascontiguousarray(base[np.arange(count) % 64])
+    job = cv.Batch(h.ctx, count, n, hh, ww)
+    job.upload_images(imgs)
+    job.save_images()
+
+    def run():
+        job.restore_images()
+        job.init_checkerboard()
+        npm = job.perona_malik(**c["pm"])
+        steps, _ = job.csv_run(prm, tol=tol, max_steps=max_steps)
+        return npm, steps
+
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(h.stream)
+    reps = 2
+    for _ in range(reps):
+        npm, steps = run()
+    e1.record(h.stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pixit = float(hh) * ww * (npm * count + int(steps.sum()))
+    peak, _ = measured_peak()
+    alg = (BYTES_CSV_RGB * int(steps.sum()) + BYTES_PM_RGB * npm * count) * hh * ww
+    res = {"images": count, "h": hh, "w": ww, "pm_steps": npm, "csv_steps_min": int(steps.min()), "csv_steps_max": int(steps.max()),
+           "csv_steps_mean": float(steps.mean()), "ms": ms, "pixel_iters_per_s": pixit / (ms * 1e-3),
+           "frac_hbm": alg / (ms * 1e-3) / 1e9 / peak,
+           "what": "%d of the 4096 images of configs[4] as one batch job on this GPU (the share of one rank of 8); "
+                   "the whole batch on N GPUs: bench.py --workload batch" % count}
+    job.close()
+    return res
+
+
 def time_oneshot(h, views):
     """cvb_segment: one call, pageable host buffers, fp64 u in and out, PM planes and the byte mask out."""
     import numpy as np
@@ -517,6 +564,10 @@ def run_slabs(args):
                 extra[name + ("_fp32" if fp32 else "")] = time_config(h, name, fp32=fp32, reps=2 if name == "C3" else 5)
             except Exception as e:  # an extra must never cost the headline line
                 extra[name + ("_fp32" if fp32 else "")] = {"error": repr(e)}
+        try:
+            extra["C5_512"] = time_batch_sample(h)
+        except Exception as e:
+            extra["C5_512"] = {"error": repr(e)}
         try:
             extra["e2e_oneshot"] = time_oneshot(h, views)
         except Exception as e:
