@@ -8,9 +8,13 @@
 // installed in this image, so files are binary PNM (P6 colour, P5 gray); the two functions read_image/write_image
 // are the only place an OpenCV-linked build would change.  The interactive -R/-C contour selection (a GUI window,
 // src/main.cpp:899-921) becomes --rect x,y,w,h / --circ cx,cy,r with the same level sets
-// (InteractiveDataRect.cpp:20-27, InteractiveDataCirc.cpp:18-25).  -V writes the contour of the FINAL level set
-// over the image as "<stem>_contour<ext>" (the reference's XVID video needs highgui); the contour rule is
-// VideoWriterManager's threshold saturate_cast<uchar>(u) > 0 (src/VideoWriterManager.cpp:65-68).
+// (InteractiveDataRect.cpp:20-27, InteractiveDataCirc.cpp:18-25).  -V: the reference writes "<stem>.avi" (XVID through
+// highgui, src/VideoWriterManager.cpp:24-54) with frame 0 = the initial contour and one frame per step (src/main.cpp:929,
+// :997); without a video encoder on this host the same frames go, uncompressed, into "<stem>.ppms" -- binary PPM images
+// back to back (`ffmpeg -f image2pipe -vcodec ppm -r <fps> -i <stem>.ppms out.avi` encodes them) -- fed by the
+// asynchronous per-step mask observer of the ABI (cvb_csv_run_masks, CVB_MASK_CONTOUR = VideoWriterManager's threshold
+// saturate_cast<uchar>(u) > 0, :65-68); the contour of the FINAL level set is also written as "<stem>_contour<ext>".
+// Overlay text (-O) needs a font renderer and is not drawn.
 #include <sys/stat.h>
 
 #include <cmath>
@@ -146,7 +150,7 @@ const char *kHelp =
     "  -e [ --epsilon ] arg (=1)       smoothing parameter in Heaviside/delta\n"
     "  -t [ --tolerance ] arg (=0.001) tolerance in stopping condition\n"
     "  -N [ --max-steps ] arg (=-1)    maximum nof iterations (negative means unlimited)\n"
-    "  -f [ --fps ] arg (=10)          video fps (accepted, unused: no video encoder on this host)\n"
+    "  -f [ --fps ] arg (=10)          video fps (accepted; the frame stream <stem>.ppms carries no timing)\n"
     "  -P [ --overlay-pos ] arg (=TL)  overlay tex position; allowed only: TL, BL, TR, BR\n"
     "  -l [ --line-color ] arg (=blue) contour color (allowed only: black, white, R, G, B, Y, M, C\n"
     "  -K [ --edge-coef ] arg (=10)    coefficient for enhancing edge detection in Perona-Malik\n"
@@ -154,7 +158,7 @@ const char *kHelp =
     "  -T [ --segment-time ] arg (=20) number of smoothing steps in Perona-Malik\n"
     "  -S [ --segment ]                segment the image with Perona-Malik beforehand\n"
     "  -g [ --grayscale ]              read in as grayscale\n"
-    "  -V [ --video ]                  write the final contour over the image (adds suffix '_contour')\n"
+    "  -V [ --video ]                  per-step contour frames as <stem>.ppms (PPM stream) + the final contour ('_contour')\n"
     "  -O [ --overlay-text ]           add overlay text (accepted, unused)\n"
     "  -I [ --invert-selection ]       invert selected region (see: select)\n"
     "  -s [ --select ]                 separate the region encolosed by the contour (adds suffix '_selection')\n"
@@ -392,9 +396,68 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> mask(np);
     int steps = 0;
     double norm = 0;
-    // PM (optional) + the time-step loop + separate()'s mask in one resident pass (src/main.cpp:939-1001)
-    check(cvb_segment(ctx, planes.data(), n, h, w, u.data(), o.segment ? 1 : 0, o.K, o.L, o.T, pm_ptrs.data(), &p, o.tol,
-                      o.max_steps, &steps, &norm, o.invert ? 1 : 0, mask.data()));
+    // contour of a 0/1 mask over the ORIGINAL image (VideoWriterManager draws over img, :43-45): mask pixels with a
+    // 4-neighbour outside the mask take the contour colour
+    auto draw = [&](const std::vector<uint8_t> &m01, std::vector<std::vector<uint8_t>> &fr) {
+        for (int k = 0; k < 3; ++k) fr[k] = img.planes[n == 3 ? k : 0];
+        auto in = [&](int i, int j) { return i >= 0 && i < h && j >= 0 && j < w && m01[(size_t)i * w + j]; };
+        for (int i = 0; i < h; ++i)
+            for (int j = 0; j < w; ++j)
+                if (in(i, j) && !(in(i - 1, j) && in(i + 1, j) && in(i, j - 1) && in(i, j + 1)))
+                    for (int k = 0; k < 3; ++k) fr[k][(size_t)i * w + j] = color[k];
+    };
+    if (!o.video) {
+        // PM (optional) + the time-step loop + separate()'s mask in one resident pass (src/main.cpp:939-1001)
+        check(cvb_segment(ctx, planes.data(), n, h, w, u.data(), o.segment ? 1 : 0, o.K, o.L, o.T, pm_ptrs.data(), &p, o.tol,
+                          o.max_steps, &steps, &norm, o.invert ? 1 : 0, mask.data()));
+    } else {
+        // the same with the per-step frame stream: frame 0 = the initial contour (:929), then one frame per step (:997)
+        struct Stream {
+            FILE *f;
+            int h, w, frames;
+            std::vector<uint8_t> m01;
+            std::vector<std::vector<uint8_t>> fr;
+            decltype(draw) *draw_fn;
+        } vs{nullptr, h, w, 0, std::vector<uint8_t>(np), std::vector<std::vector<uint8_t>>(3), &draw};
+        const size_t dot = o.input.find_last_of('.'), slash = o.input.find_last_of('/');
+        const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash);
+        const std::string vname = (has_ext ? o.input.substr(0, dot) : o.input) + ".ppms";
+        vs.f = std::fopen(vname.c_str(), "wb");
+        if (!vs.f) msg_exit("Error: cannot open \"" + vname + "\" for writing");
+        auto put = [](Stream &v) {
+            (*v.draw_fn)(v.m01, v.fr);
+            std::fprintf(v.f, "P6\n%d %d\n255\n", v.w, v.h);
+            std::vector<uint8_t> rgb((size_t)v.h * v.w * 3);
+            for (size_t q = 0; q < (size_t)v.h * v.w; ++q) {
+                rgb[3 * q] = v.fr[2][q];
+                rgb[3 * q + 1] = v.fr[1][q];
+                rgb[3 * q + 2] = v.fr[0][q];
+            }
+            std::fwrite(rgb.data(), 1, rgb.size(), v.f);
+            ++v.frames;
+        };
+        for (size_t q = 0; q < np; ++q) vs.m01[q] = std::nearbyint(u[q]) > 0;  // saturate_cast<uchar>(u) > 0, :65
+        put(vs);
+        static auto put_fn = +put;
+        auto on_mask = [](const uint8_t *bits, int hh, int ww, int /*step*/, void *user) -> int {
+            Stream &v = *static_cast<Stream *>(user);
+            const int wb = (ww + 7) / 8;
+            for (int i = 0; i < hh; ++i)
+                for (int j = 0; j < ww; ++j) v.m01[(size_t)i * ww + j] = (bits[(size_t)i * wb + j / 8] >> (7 - j % 8)) & 1;
+            put_fn(v);
+            return 0;
+        };
+        const uint8_t *const *cur = planes.data();
+        std::vector<const uint8_t *> pm_c;
+        if (o.segment) {
+            check(cvb_perona_malik(ctx, planes.data(), n, h, w, o.K, o.L, o.T, pm_ptrs.data(), nullptr));
+            for (auto &pl : pm) pm_c.push_back(pl.data());
+            cur = pm_c.data();
+        }
+        check(cvb_csv_run_masks(ctx, cur, n, h, w, u.data(), &p, o.tol, o.max_steps, &steps, &norm, CVB_MASK_CONTOUR, +on_mask, &vs));
+        std::fclose(vs.f);
+        check(cvb_mask(ctx, u.data(), h, w, o.invert ? 1 : 0, mask.data()));
+    }
     if (o.segment) {  // cv::imwrite(add_suffix(input_filename, "pm"), smoothed_img), :946
         std::vector<const uint8_t *> out;
         for (auto &pl : pm) out.push_back(pl.data());
@@ -409,12 +472,9 @@ int main(int argc, char **argv) {
     }
     if (o.video) {  // contour of the final level set: pixels of {u > 0.5} with a 4-neighbour outside it
         std::vector<std::vector<uint8_t>> fr(3);
-        for (int k = 0; k < 3; ++k) fr[k] = img.planes[n == 3 ? k : 0];
-        auto in = [&](int i, int j) { return i >= 0 && i < h && j >= 0 && j < w && std::nearbyint(u[(size_t)i * w + j]) > 0; };
-        for (int i = 0; i < h; ++i)
-            for (int j = 0; j < w; ++j)
-                if (in(i, j) && !(in(i - 1, j) && in(i + 1, j) && in(i, j - 1) && in(i, j + 1)))
-                    for (int k = 0; k < 3; ++k) fr[k][(size_t)i * w + j] = color[k];
+        std::vector<uint8_t> m01(np);
+        for (size_t q = 0; q < np; ++q) m01[q] = std::nearbyint(u[q]) > 0;
+        draw(m01, fr);
         write_image(add_suffix(o.input, "contour"), {fr[0].data(), fr[1].data(), fr[2].data()}, h, w);
     }
     if (o.stats) {

@@ -86,6 +86,15 @@ def test_cli_end_to_end_matches_binding(cli, tmp_path, ctx):
         assert np.array_equal(sel[k][m], planes[k][m]) and np.all(sel[k][~m] == 255)
     assert os.path.exists(tmp_path / "star_contour.ppm")
     assert "steps=%d " % ref["steps"] in r.stderr
+    # -V: the per-step frame stream (PPM images back to back): frame 0 + one frame per step (src/main.cpp:929, :997), fed by
+    # the asynchronous mask observer; the last frame shows the contour of the final level set
+    raw = open(tmp_path / "star.ppms", "rb").read()
+    head = b"P6\n150 120\n255\n"
+    fsz = len(head) + 120 * 150 * 3
+    assert len(raw) == (1 + ref["steps"]) * fsz and all(raw[k * fsz:k * fsz + len(head)] == head for k in range(1 + ref["steps"]))
+    assert raw[-fsz:] == open(tmp_path / "star_contour.ppm", "rb").read()
+    first = np.frombuffer(raw[len(head):fsz], dtype=np.uint8).reshape(120, 150, 3)
+    assert (first != np.stack([planes[2], planes[1], planes[0]], axis=-1)).any()  # the checkerboard's contour is drawn
     # grayscale + non-interactive circle init + inverted selection
     r = _run(cli, "-i", str(img), "-g", "-s", "-I", "-N", "10", "--circ", "75,60,30")
     assert r.returncode == 0, r.stderr
