@@ -121,3 +121,44 @@ def test_slab_spans_match_group_ownership():
                 lo, hi = cv.slab_partition(h, rows, world, r)
                 g0, g1 = r * 32 // world, (r + 1) * 32 // world
                 assert lo == min(-(-g0 * nseg // 32) * rows, h) and hi == min(-(-g1 * nseg // 32) * rows, h)
+
+
+# ---- bench.py's result digest across ranks (gloo, world_size 2): per-rank CRCs gathered with all_gather_object and
+# combined in rank order equal the CRC of the whole image, for the automatic (rank-count independent) tile length ----------
+def _digest_worker(rank, world, port, out):
+    import sys
+    import zlib
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    h, w = 9000, 4000
+    tile = cv.auto_tile_rows(h, w, 1, world)
+    assert tile == cv.auto_tile_rows(h, w, 1, 1)  # the same tiling on every rank count
+    lo, hi = cv.slab_partition(h, tile, world, rank)
+    planes = synth.hashed_scene_rows(h, w, lo, hi, cell=512)
+    u = np.cos(np.arange(lo, hi, dtype=np.float64))[:, None] * np.arange(w, dtype=np.float64)[None, :]
+    parts = [bench.crc_of(p) for p in planes] + [bench.crc_of(u)]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, parts)
+    if rank == 0:
+        whole = synth.hashed_scene_rows(h, w, 0, h, cell=512)
+        uw = np.cos(np.arange(h, dtype=np.float64))[:, None] * np.arange(w, dtype=np.float64)[None, :]
+        want = [zlib.crc32(p.tobytes()) for p in whole] + [zlib.crc32(uw.tobytes())]
+        out.put(bench.combine_ranks(gathered) == want)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_digest_over_two_gloo_ranks():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_digest_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok and all(p.exitcode == 0 for p in procs)

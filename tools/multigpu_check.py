@@ -8,7 +8,8 @@ The geometry of bench.py (the open 8-GPU item of DESIGN.md section 5) is reprodu
     ... tools/multigpu_check.py --size 16384 --square --tiles world --pm-T 5 --csv-steps 100 --repeat 3 --trace
 (tiles chosen for the rank count as bench.py does, 20 PM + 100 CSV steps, the resident sequence with save / restore
 repeated, the end-to-end sequence with the bit-packed mask, a trace line per phase and rank on stderr).
-Beyond 2 ranks upload_image_smooth defaults to the plain sequence; CVB_OVERLAP_UPLOAD=1 exercises the overlapped one.
+Programmatic dependent launch and the overlapped upload are on at every rank count (CVB_PDL=0 / CVB_OVERLAP_UPLOAD=0 turn
+them off).  Soak: `--repeat 50` repeats the resident sequence 50 times before the comparison (round 2: PASS on 8 GPUs).
 """
 import argparse
 import os
