@@ -1,14 +1,15 @@
 // Device side of the NCCL-free multi-GPU step loop: release/acquire flags in peer memory over NVLink.
 //
 // Row-slab protocol (one process per GPU, peers' buffers mapped with CUDA IPC):
-//   * a CTA that writes one of the slab's first/last HALO rows also stores it into the neighbour's halo rows;
-//   * the warp that completes the last local reduction group copies this rank's group sums into every peer's
-//     group-sum array and then bumps arrive[rank] in every peer's CommBox (st.release.sys after a system fence);
-//   * the NEXT launch starts by folding the newest reduction: the first warp to get there waits until all ranks
-//     have arrived, adds the 32 group sums in index order (identical on every rank => bit-identical c1/c2 and stop
-//     decision everywhere), publishes `finalized`; every other warp waits for that before touching c1/c2 or halo rows.
-// Nothing ever waits for a kernel on the SAME GPU that might not be resident: the folding warp is elected among
-// the warps that are running, and peers only wait for the previous launch of their neighbours.
+//   * a CTA that writes one of the slab's first/last HALO rows also stores it into the neighbour's halo rows (those CTAs
+//     are scheduled first, csv_kernels.cu);
+//   * the warp that completes the last local reduction group copies this rank's group sums into every peer's group-sum
+//     array, raises arrive[rank] in every peer's CommBox (st.release.sys after a warp barrier) and then -- in the tail of
+//     the SAME launch -- waits until all ranks have arrived and adds the 32 group sums in index order (identical on every
+//     rank => bit-identical c1/c2 and stop decision everywhere): a CSV step is one launch on every rank (reduce.cuh);
+//   * PM: the last boundary CTA of a launch raises the neighbour's flag, pm_wait_kernel polls it before the next launch.
+// Nothing ever waits for a kernel on the SAME GPU that might not be resident, and peers only wait for launches that are
+// queued before anything that waits for them.  Every wait is bounded (spin_until).
 #pragma once
 #include "common.cuh"
 
