@@ -11,8 +11,10 @@
 // and u(i) - u(i-1) are carried in registers from the previous row.  Lane 0 is a halo lane (it supplies nx of the
 // column left of the strip), so a strip owns 62 columns.  Production path (csv_rows_ring): rows stream
 // HBM -> shared memory through a cp.async ring 7 rows ahead of the row being computed, east / west neighbours are
-// read from the ring.  Generic path (strict math, curvature-only mode): explicit clamps, register prefetch CSV_D rows
-// ahead and L2 prefetch CSV_PF rows ahead.
+// read from the ring; a CTA may march through several segments and delivers the fused sums per segment
+// (Geom::seg_mult).  Build variant -DCSV_TMA (csv_rows_tma): the same loop fed by cp.async.bulk.tensor + mbarrier --
+// measured equal (profiles/README.md), not the default.  Generic path (strict math, curvature-only mode): explicit
+// clamps, register prefetch CSV_D rows ahead and L2 prefetch CSV_PF rows ahead.
 #include <limits.h>
 #include <string.h>
 

@@ -11,7 +11,8 @@
 // 31 are halo lanes: a strip owns 60 columns.  fp64 planes stream through a cp.async shared-memory ring
 // (pm_rows_ring: east / west neighbours of I are read from the ring, g and the west flux come from the neighbouring
 // lanes by shuffle); the uint8-input first step and the strict path march rows through registers (pm_rows_fast,
-// pm_rows_generic).
+// pm_rows_generic).  pm2_step_kernel (pm2_rows_ring) runs TWO diffusion steps per launch -- temporal blocking: the
+// intermediate rows never leave the SM -- and is what every pair of fp64 -> fp64 steps goes through.
 #include <string.h>
 
 #include "async_copy.cuh"
