@@ -198,16 +198,18 @@ def run_reference(args):
     if rank != 0:
         return
     value, desc, cores, sec = cpu_sample(args.cpu_size, args.steps, args.warmup)
-    cfg = workload_config(args, 1)
-    # what this arm times is a bounded sample of that workload: say so where the workload is named
-    cfg["workload"] = "%dx%d-crop sample (PM 2 + CSV 10 steps per sample step, same 1:5 ratio) of " % (args.cpu_size, args.cpu_size) + cfg["workload"]
-    cfg["sample"] = {"h": args.cpu_size, "w": args.cpu_size, "pm_steps": 2, "csv_steps": 10}
-    cfg["decomposition"] = "host cores only (no GPU)"
-    cfg.pop("l2", None)
+    # `config` is the b200 arm's config of the same command line, key for key (the measurement contract: the reference
+    # arm runs "on your arm's config"); WHAT of that workload a step of this arm times is said next to it, in `sample`
+    cfg = workload_config(args, max(args.gpus, 1))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
+            "sample": {"of": cfg["workload"], "h": args.cpu_size, "w": args.cpu_size, "pm_steps": 2, "csv_steps": 10,
+                       "what": "every step of this arm is a %dx%d crop of the workload's scene, PM 2 + CSV 10 steps (the "
+                               "workload's 1:5 ratio), on the host cores only; the value is per pixel-iteration, so it compares "
+                               "with the b200 arm's (a smaller working set favours the CPU: the ratio is conservative)"
+                               % (args.cpu_size, args.cpu_size)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
